@@ -1,0 +1,110 @@
+/*
+ * mrg_lstm.h — C-ABI of the B200 (sm_100a) LSTM hot path of MultimodalReactionGeneration.
+ *
+ * The reference has no FFI layer: every LSTM call is `torch.nn.LSTM(...)(x, hx)` held by three
+ * thin wrappers.  These entry points are what a binding for that seam calls instead:
+ *
+ *   mrg_lstm_layer_forward / _backward   replace  nn.LSTM.forward and its autograd backward at
+ *       mr_gen/model/utils/lstm_block.py:21,41    (LSTMModule.lstm_module)
+ *       mr_gen/model/utils/lstm_sampler.py:16,29  (LSTMSampler.sampler)
+ *       mr_gen/model/utils/mixer_block.py:237,251 (LSTMMixer.mixer)
+ *   mrg_rollout_forward / _backward      replace the Python time loop of
+ *       mr_gen/model/lstm_with_sampling/lstm_with_sample.py:379-408 (head_motion_generation)
+ *       + :410-433 (generate_one_step) with one persistent kernel
+ *   mrg_philox_mask                      replaces `torch.rand(length) < epoch/max_epochs`
+ *       mr_gen/model/lstm_with_sampling/lstm_with_sample.py:389
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer to fp32 data owned by
+ * the caller (a torch tensor) unless stated otherwise, and must stay alive until the work queued on
+ * `stream` (a cudaStream_t passed as void*) has finished.  All calls are asynchronous on `stream`.
+ * Return value: 0 = OK, <0 = invalid argument (MRG_E_*), >0 = cudaError_t.  No exceptions cross the
+ * boundary; mrg_last_error_string() describes the last failure on the calling thread.
+ *
+ * Tensor layouts (all contiguous, fp32):
+ *   x       [T][B][I]            time-major input of the layer
+ *   w_ih    [4H][I], w_hh [4H][H], b_* [4H]   torch.nn.LSTM layout, gate order i,f,g,o (rnn.py:842-847)
+ *   gates   [D][T][B][H][4]      reserve: post-activation (i,f,g,o) per hidden unit, gate-interleaved;
+ *                                the backward overwrites it with d(pre-activation)
+ *   y_ext   [D][T+1][B][H]       hidden states with one extra slot for h0:
+ *                                  direction 0 (forward in time): slot 0 = h0, slot t+1 = h_t
+ *                                  direction 1 (reverse):          slot T = h0, slot t   = h_t
+ *   c_ext   [D][T+1][B][H]       cell states, same slot convention
+ */
+#ifndef MRG_LSTM_H_
+#define MRG_LSTM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRG_VERSION 100
+
+#define MRG_E_INVALID   (-1)  /* bad shape / null pointer */
+#define MRG_E_UNSUPPORTED (-2)
+#define MRG_E_WORKSPACE (-3)  /* workspace too small */
+
+/* flags */
+#define MRG_F_TRAIN        1   /* forward: keep gates / c for the backward                     */
+#define MRG_F_GENERIC_REC  2   /* force the generic (non-cluster) recurrent kernels             */
+#define MRG_F_SIMT_GEMM    4   /* force the SIMT fp32 GEMM instead of the tcgen05 3xTF32 GEMM   */
+#define MRG_F_ACCUMULATE   8   /* backward: add into dw_ih / dw_hh / db instead of overwriting  */
+
+typedef struct mrg_lstm_dir_weights {
+  const float* w_ih;  /* [4H][I] */
+  const float* w_hh;  /* [4H][H] */
+  const float* b_ih;  /* [4H] or NULL */
+  const float* b_hh;  /* [4H] or NULL */
+  const float* h0;    /* [B][H] or NULL (zeros) */
+  const float* c0;    /* [B][H] or NULL (zeros) */
+} mrg_lstm_dir_weights;
+
+typedef struct mrg_lstm_dir_grads {
+  float* dw_ih;  /* [4H][I] */
+  float* dw_hh;  /* [4H][H] */
+  float* db;     /* [4H]  gradient of b_ih and of b_hh (they enter as a sum) */
+  float* dh0;    /* [B][H] or NULL */
+  float* dc0;    /* [B][H] or NULL */
+} mrg_lstm_dir_grads;
+
+int mrg_version(void);
+const char* mrg_last_error_string(void);
+
+/* Device facts the host side sizes its launches with. Returns 0 and fills the outputs. */
+int mrg_device_info(int* sm_count, int* max_clusters_h256, int* max_clusters_h128, int* cc_major,
+                    int* cc_minor);
+
+/* Bytes of scratch mrg_lstm_layer_forward / _backward need for this shape (max of both). */
+size_t mrg_lstm_workspace_bytes(int T, int B, int I, int H, int D);
+
+/* One nn.LSTM layer, D = 1 (uni) or 2 (bidirectional) directions in one launch.
+ * w_pack: caller-owned buffer of D*4H*I floats; receives W_ih with gate-interleaved rows and is
+ * consumed again by the backward. */
+int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights* w, float* w_pack, float* gates,
+                           float* y_ext, float* c_ext, void* workspace, size_t workspace_bytes, int T,
+                           int B, int I, int H, int D, int flags, void* stream);
+
+/* BPTT of the same layer.  dy is [T][B][D*H] (NULL = zeros); dh_n/dc_n are [D][B][H] or NULL.
+ * dx [T][B][I] may be NULL when the input needs no gradient. */
+int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weights* w, const float* w_pack,
+                            const float* dy, const float* dh_n, const float* dc_n, float* gates,
+                            const float* y_ext, const float* c_ext, float* dx,
+                            const mrg_lstm_dir_grads* g, void* workspace, size_t workspace_bytes, int T,
+                            int B, int I, int H, int D, int flags, void* stream);
+
+/* C[M][N] = A[M][K] * B[N][K]^T (+ bias[N]) — the time-parallel projection GEMM, exported for tests
+ * and for the Linear layers adjacent to the LSTMs. */
+int mrg_gemm_nt(const float* a, const float* b, const float* bias, float* c, int M, int N, int K,
+                void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* Scheduled-sampling mask: out[t*B+b] = philox4x32_10(ctr=(lo(offset+t), hi(offset+t), shared?0:b, 0),
+ * key=(lo(seed), hi(seed)))[0] >> 8 as a 24-bit uniform < prob.  out is a DEVICE uint8 buffer. */
+int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared, uint8_t* out,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRG_LSTM_H_ */

@@ -1,0 +1,77 @@
+"""ctypes binding of include/mrg_lstm.h (the C-ABI shared library built from csrc/)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint8, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libmrg_b200.so")
+
+F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE = 1, 2, 4, 8
+
+EXPORTS = (
+    "mrg_version", "mrg_last_error_string", "mrg_device_info", "mrg_lstm_workspace_bytes",
+    "mrg_lstm_layer_forward", "mrg_lstm_layer_backward", "mrg_gemm_nt", "mrg_philox_mask",
+)
+
+
+class DirWeights(ctypes.Structure):
+    _fields_ = [("w_ih", c_void_p), ("w_hh", c_void_p), ("b_ih", c_void_p), ("b_hh", c_void_p),
+                ("h0", c_void_p), ("c0", c_void_p)]
+
+
+class DirGrads(ctypes.Structure):
+    _fields_ = [("dw_ih", c_void_p), ("dw_hh", c_void_p), ("db", c_void_p), ("dh0", c_void_p),
+                ("dc0", c_void_p)]
+
+
+class MrgError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the extension; fail loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise MrgError(
+            f"{LIB_PATH} is missing: build it with `python -m multimodalreactiongeneration_b200._build` "
+            "(there is no CPU / PyTorch fallback for the LSTM path)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.mrg_version.restype = c_int
+    L.mrg_last_error_string.restype = c_char_p
+    L.mrg_device_info.argtypes = [POINTER(c_int)] * 5
+    L.mrg_device_info.restype = c_int
+    L.mrg_lstm_workspace_bytes.argtypes = [c_int] * 5
+    L.mrg_lstm_workspace_bytes.restype = c_size_t
+    L.mrg_lstm_layer_forward.argtypes = [
+        c_void_p, POINTER(DirWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    L.mrg_lstm_layer_forward.restype = c_int
+    L.mrg_lstm_layer_backward.argtypes = [
+        c_void_p, POINTER(DirWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+        c_void_p, c_void_p, POINTER(DirGrads), c_void_p, c_size_t,
+        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    L.mrg_lstm_layer_backward.restype = c_int
+    L.mrg_gemm_nt.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                              c_size_t, c_int, c_void_p]
+    L.mrg_gemm_nt.restype = c_int
+    L.mrg_philox_mask.argtypes = [c_uint64, c_uint64, c_float, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.mrg_philox_mask.restype = c_int
+    _LIB = L
+    return L
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().mrg_last_error_string().decode("utf-8", "replace")
+        raise MrgError(f"{what} failed with status {status}: {msg}")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()

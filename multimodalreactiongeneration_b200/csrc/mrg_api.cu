@@ -1,0 +1,217 @@
+// C-ABI entry points (include/mrg_lstm.h): orchestration of pack -> projection GEMM -> recurrent
+// kernel for the forward, and recurrent BPTT kernel -> dX / dW GEMMs -> bias column sums for the
+// backward.  Everything is queued on the caller's stream; nothing synchronises.
+#include "mrg_common.cuh"
+
+namespace mrg {
+int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+bool gemm_tc_supported(const GemmArgs& g);
+size_t gemm_tc_workspace_bytes(int M, int N, int K);
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int run_gemm(const GemmArgs& g, void* ws, size_t ws_bytes, int flags, cudaStream_t stream) {
+#ifdef MRG_HAVE_TC_GEMM
+  if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) return gemm_tc(g, ws, ws_bytes, stream);
+#endif
+  return gemm_simt(g, ws, ws_bytes, stream);
+}
+
+static size_t gemm_ws(int M, int N, int K) {
+  size_t s = gemm_simt_workspace_bytes(M, N, K);
+#ifdef MRG_HAVE_TC_GEMM
+  const size_t t = gemm_tc_workspace_bytes(M, N, K);
+  if (t > s) s = t;
+#endif
+  return s;
+}
+
+static int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    } else {
+      ok = (p.major == 10) ? 1 : 0;
+    }
+  }
+  return ok;
+}
+
+}  // namespace mrg
+
+using namespace mrg;
+
+extern "C" int mrg_device_info(int* sm_count, int* max_clusters_h256, int* max_clusters_h128,
+                               int* cc_major, int* cc_minor) {
+  int dev = 0;
+  MRG_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  MRG_CUDA_CHECK(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (max_clusters_h256) *max_clusters_h256 = max_active_clusters(256);
+  if (max_clusters_h128) *max_clusters_h128 = max_active_clusters(128);
+  return 0;
+}
+
+extern "C" size_t mrg_lstm_workspace_bytes(int T, int B, int I, int H, int D) {
+  if (T < 0 || B <= 0 || I <= 0 || H <= 0 || D < 1 || D > 2) return 0;
+  const size_t head = align_up((size_t)D * 4 * H * sizeof(float), 256) +
+                      align_up((size_t)D * B * 4 * H * sizeof(float), 256);
+  size_t g = gemm_ws(T * B, 4 * H, I);
+  size_t v = gemm_ws(T * B, I, 4 * H);
+  if (v > g) g = v;
+  v = gemm_ws(4 * H, I, T * B);
+  if (v > g) g = v;
+  v = gemm_ws(4 * H, H, T * B);
+  if (v > g) g = v;
+  return head + align_up(g, 256) + 256;
+}
+
+static int check_shape(const char* who, int T, int B, int I, int H, int D) {
+  MRG_REQUIRE(T >= 0 && B > 0 && I > 0 && H > 0 && (D == 1 || D == 2),
+              "%s: bad shape T=%d B=%d I=%d H=%d D=%d", who, T, B, I, H, D);
+  MRG_REQUIRE(check_device() == 1, "%s: this library only runs on compute capability 10.x (B200)", who);
+  return 0;
+}
+
+extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights* w, float* w_pack,
+                                      float* gates, float* y_ext, float* c_ext, void* workspace,
+                                      size_t workspace_bytes, int T, int B, int I, int H, int D, int flags,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_shape("mrg_lstm_layer_forward", T, B, I, H, D)) return e;
+  MRG_REQUIRE(w && w_pack && gates && y_ext && c_ext && (x || T == 0), "mrg_lstm_layer_forward: null pointer");
+  for (int d = 0; d < D; ++d)
+    MRG_REQUIRE(w[d].w_ih && w[d].w_hh, "mrg_lstm_layer_forward: null weights for direction %d", d);
+  if (workspace_bytes < mrg_lstm_workspace_bytes(T, B, I, H, D) || workspace == nullptr) {
+    set_error("mrg_lstm_layer_forward: workspace too small");
+    return MRG_E_WORKSPACE;
+  }
+  char* ws = (char*)workspace;
+  float* bias_pack = (float*)ws;
+  ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
+  ws += align_up((size_t)D * B * 4 * H * sizeof(float), 256);
+  const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+
+  if (int e = pack_weights(w, w_pack, bias_pack, I, H, D, stream)) return e;
+  const size_t slot = (size_t)B * H;
+  for (int d = 0; d < D; ++d) {
+    float* ys = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : (size_t)T * slot);
+    float* cs = c_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : (size_t)T * slot);
+    if (w[d].h0) MRG_CUDA_CHECK(cudaMemcpyAsync(ys, w[d].h0, slot * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    else MRG_CUDA_CHECK(cudaMemsetAsync(ys, 0, slot * sizeof(float), stream));
+    if (w[d].c0) MRG_CUDA_CHECK(cudaMemcpyAsync(cs, w[d].c0, slot * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    else MRG_CUDA_CHECK(cudaMemsetAsync(cs, 0, slot * sizeof(float), stream));
+  }
+  if (T == 0) return 0;
+  for (int d = 0; d < D; ++d) {
+    GemmArgs g = {};
+    g.a = x; g.a_sm = I; g.a_sk = 1;
+    g.b = w_pack + (size_t)d * 4 * H * I; g.b_sk = 1; g.b_sn = I;
+    g.bias = bias_pack + (size_t)d * 4 * H;
+    g.c = gates + (size_t)d * T * B * 4 * H; g.ldc = 4 * H;
+    g.M = T * B; g.N = 4 * H; g.K = I;
+    if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
+  }
+  RecArgs r = {};
+  r.gates = gates;
+  r.w_hh[0] = w[0].w_hh;
+  r.w_hh[1] = D > 1 ? w[1].w_hh : nullptr;
+  r.y_ext = y_ext; r.c_ext = c_ext;
+  r.T = T; r.B = B; r.H = H; r.D = D;
+  r.train = (flags & MRG_F_TRAIN) ? 1 : 0;
+  if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) return rec_forward_cluster(r, stream);
+  return rec_forward_generic(r, stream);
+}
+
+extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weights* w, const float* w_pack,
+                                       const float* dy, const float* dh_n, const float* dc_n, float* gates,
+                                       const float* y_ext, const float* c_ext, float* dx,
+                                       const mrg_lstm_dir_grads* g, void* workspace, size_t workspace_bytes,
+                                       int T, int B, int I, int H, int D, int flags, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_shape("mrg_lstm_layer_backward", T, B, I, H, D)) return e;
+  MRG_REQUIRE(w && w_pack && gates && y_ext && c_ext && g && (x || T == 0),
+              "mrg_lstm_layer_backward: null pointer");
+  if (workspace_bytes < mrg_lstm_workspace_bytes(T, B, I, H, D) || workspace == nullptr) {
+    set_error("mrg_lstm_layer_backward: workspace too small");
+    return MRG_E_WORKSPACE;
+  }
+  char* ws = (char*)workspace;
+  ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
+  float* db_part = (float*)ws;
+  ws += align_up((size_t)D * B * 4 * H * sizeof(float), 256);
+  const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  const int acc = (flags & MRG_F_ACCUMULATE) ? 1 : 0;
+
+  RecBwdArgs r = {};
+  r.gates = gates;
+  r.w_hh[0] = w[0].w_hh;
+  r.w_hh[1] = D > 1 ? w[1].w_hh : nullptr;
+  r.y_ext = y_ext; r.c_ext = c_ext;
+  r.dy = dy; r.dh_n = dh_n; r.dc_n = dc_n;
+  for (int d = 0; d < 2; ++d) {
+    r.dh0[d] = d < D ? g[d].dh0 : nullptr;
+    r.dc0[d] = d < D ? g[d].dc0 : nullptr;
+  }
+  r.db_part = db_part;
+  r.T = T; r.B = B; r.H = H; r.D = D;
+  int e;
+  if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) e = rec_backward_cluster(r, stream);
+  else e = rec_backward_generic(r, stream);
+  if (e) return e;
+
+  const size_t slot = (size_t)B * H;
+  for (int d = 0; d < D; ++d) {
+    const float* dpre = gates + (size_t)d * T * B * 4 * H;
+    if (g[d].db)
+      if ((e = colsum_deinterleave(db_part + (size_t)d * B * 4 * H, g[d].db, B, H, acc, stream))) return e;
+    if (g[d].dw_ih) {
+      GemmArgs m = {};
+      m.a = dpre; m.a_sm = 1; m.a_sk = 4 * H;
+      m.b = x; m.b_sk = I; m.b_sn = 1;
+      m.c = g[d].dw_ih; m.ldc = I;
+      m.M = 4 * H; m.N = I; m.K = T * B;
+      m.accumulate = acc; m.row_deinterleave_H = H;
+      if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
+    }
+    if (g[d].dw_hh) {
+      const float* hprev = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : slot);
+      GemmArgs m = {};
+      m.a = dpre; m.a_sm = 1; m.a_sk = 4 * H;
+      m.b = hprev; m.b_sk = H; m.b_sn = 1;
+      m.c = g[d].dw_hh; m.ldc = H;
+      m.M = 4 * H; m.N = H; m.K = T * B;
+      m.accumulate = acc; m.row_deinterleave_H = H;
+      if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
+    }
+    if (dx) {
+      GemmArgs m = {};
+      m.a = dpre; m.a_sm = 4 * H; m.a_sk = 1;
+      m.b = w_pack + (size_t)d * 4 * H * I; m.b_sk = I; m.b_sn = 1;
+      m.c = dx; m.ldc = I;
+      m.M = T * B; m.N = I; m.K = 4 * H;
+      m.accumulate = d > 0 ? 1 : 0;
+      if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
+    }
+  }
+  return 0;
+}
+
+extern "C" int mrg_gemm_nt(const float* a, const float* b, const float* bias, float* c, int M, int N, int K,
+                           void* workspace, size_t workspace_bytes, int flags, void* stream) {
+  MRG_REQUIRE(a && b && c && M >= 0 && N >= 0 && K >= 0, "mrg_gemm_nt: bad arguments");
+  MRG_REQUIRE(check_device() == 1, "mrg_gemm_nt: this library only runs on compute capability 10.x (B200)");
+  GemmArgs g = {};
+  g.a = a; g.a_sm = K; g.a_sk = 1;
+  g.b = b; g.b_sk = 1; g.b_sn = K;
+  g.bias = bias; g.c = c; g.ldc = N;
+  g.M = M; g.N = N; g.K = K;
+  return run_gemm(g, workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}

@@ -1,0 +1,138 @@
+// Shared helpers for the sm_100a kernels of the LSTM hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mrg_lstm.h"
+
+namespace mrg {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define MRG_CUDA_CHECK(expr)                                                           \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      mrg::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                        \
+      return (int)_e;                                                                  \
+    }                                                                                  \
+  } while (0)
+
+#define MRG_REQUIRE(cond, ...)     \
+  do {                             \
+    if (!(cond)) {                 \
+      mrg::set_error(__VA_ARGS__); \
+      return MRG_E_INVALID;        \
+    }                              \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive_release();
+  cluster_wait_acquire();
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// packed fp32x2 FMA (Blackwell FFMA2): d = a * b + d on both halves
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// internal entry points (host)
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* a;  // A(m,k) = a[m*a_sm + k*a_sk]
+  long long a_sm, a_sk;
+  const float* b;  // B(k,n) = b[k*b_sk + n*b_sn]
+  long long b_sk, b_sn;
+  const float* bias;  // [N] or nullptr
+  float* c;           // C(m,n) = c[row(m)*ldc + n]
+  long long ldc;
+  int M, N, K;
+  int accumulate;      // C += result
+  int row_deinterleave_H;  // >0: output row m=(j*4+g) is stored at row g*H+j (gate de-interleave)
+};
+
+int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t gemm_simt_workspace_bytes(int M, int N, int K);
+
+int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, int I, int H, int D,
+                 cudaStream_t stream);
+
+struct RecArgs {
+  float* gates;        // [D][T][B][H][4]
+  const float* w_hh[2];
+  float* y_ext;        // [D][T+1][B][H]
+  float* c_ext;        // [D][T+1][B][H]
+  int T, B, H, D;
+  int train;
+};
+int rec_forward_generic(const RecArgs& a, cudaStream_t stream);
+int rec_forward_cluster(const RecArgs& a, cudaStream_t stream);  // H in {128, 256}
+bool rec_cluster_supported(int H);
+
+struct RecBwdArgs {
+  float* gates;         // in: gates, out: dpre   [D][T][B][H][4]
+  const float* w_hh[2];
+  const float* y_ext;
+  const float* c_ext;
+  const float* dy;      // [T][B][D*H] or nullptr
+  const float* dh_n;    // [D][B][H] or nullptr
+  const float* dc_n;    // [D][B][H] or nullptr
+  float* dh0[2];        // [B][H] or nullptr
+  float* dc0[2];
+  float* db_part;       // [D][B][H][4] per-row bias-gradient partials (sum over t)
+  int T, B, H, D;
+};
+int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
+int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream);
+
+int colsum_deinterleave(const float* part, float* db, int B, int H, int accumulate,
+                        cudaStream_t stream);
+int max_active_clusters(int H);
+
+}  // namespace mrg

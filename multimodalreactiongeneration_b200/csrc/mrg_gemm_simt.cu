@@ -1,0 +1,154 @@
+// fp32 SIMT GEMM with arbitrary operand strides, split-K and a gate-de-interleaving epilogue.
+// It is the always-available CUDA path for shapes the tcgen05 3xTF32 GEMM does not take
+// (unaligned K / tiny problems) and the cross-check for it (MRG_F_SIMT_GEMM).
+#include "mrg_common.cuh"
+
+namespace mrg {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+template <bool A_KCONTIG, bool B_NCONTIG>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g, float* __restrict__ partial, int klen) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * klen;
+  const int kend = min(g.K, kbeg + klen);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = tid + i * 256;
+      int m, k;
+      if (A_KCONTIG) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+      const int gm = m0 + m, gk = k0 + k;
+      ra[i] = (gm < g.M && gk < kend) ? g.a[(long long)gm * g.a_sm + (long long)gk * g.a_sk] : 0.f;
+      int n, kb;
+      if (B_NCONTIG) { n = e % BN; kb = e / BN; } else { kb = e % BK; n = e / BK; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      rb[i] = (gn < g.N && gkb < kend) ? g.b[(long long)gkb * g.b_sk + (long long)gn * g.b_sn] : 0.f;
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = tid + i * 256;
+      int m, k;
+      if (A_KCONTIG) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
+      As[k][m] = ra[i];
+      int n, kb;
+      if (B_NCONTIG) { n = e % BN; kb = e / BN; } else { kb = e % BK; n = e / BK; }
+      Bs[kb][n] = rb[i];
+    }
+  };
+
+  if (kbeg < kend) load_tile(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    store_tile();
+    __syncthreads();
+    if (k0 + BK < kend) load_tile(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const bool direct = (partial == nullptr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.N) continue;
+      if (direct) {
+        const int r = g.row_deinterleave_H > 0 ? ((m & 3) * g.row_deinterleave_H + (m >> 2)) : m;
+        float v = acc[i][j];
+        if (g.bias) v += g.bias[n];
+        float* o = g.c + (long long)r * g.ldc + n;
+        *o = g.accumulate ? *o + v : v;
+      } else {
+        partial[((size_t)blockIdx.z * g.M + m) * g.N + n] = acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(GemmArgs g, const float* __restrict__ partial, int splits) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)g.M * g.N) return;
+  const int m = (int)(idx / g.N), n = (int)(idx % g.N);
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += partial[(size_t)s * g.M * g.N + idx];
+  if (g.bias) v += g.bias[n];
+  const int r = g.row_deinterleave_H > 0 ? ((m & 3) * g.row_deinterleave_H + (m >> 2)) : m;
+  float* o = g.c + (long long)r * g.ldc + n;
+  *o = g.accumulate ? *o + v : v;
+}
+
+static int pick_splits(int M, int N, int K) {
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  if (tiles >= 96 || K < 1024) return 1;
+  int s = 148 / tiles;
+  const int smax = K / 256;
+  if (s > smax) s = smax;
+  if (s < 1) s = 1;
+  return s;
+}
+
+size_t gemm_simt_workspace_bytes(int M, int N, int K) {
+  const int s = pick_splits(M, N, K);
+  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+}
+
+int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  MRG_REQUIRE(g.K >= 0, "gemm: negative K");
+  const int splits = pick_splits(g.M, g.N, g.K);
+  float* partial = nullptr;
+  if (splits > 1) {
+    if (workspace_bytes < (size_t)splits * g.M * g.N * sizeof(float) || workspace == nullptr) {
+      set_error("gemm_simt: workspace too small (%zu needed)", (size_t)splits * g.M * g.N * sizeof(float));
+      return MRG_E_WORKSPACE;
+    }
+    partial = (float*)workspace;
+  }
+  int klen = (g.K + splits - 1) / splits;
+  klen = (klen + BK - 1) / BK * BK;
+  if (klen == 0) klen = BK;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
+  const bool ak = (g.a_sk == 1), bn = (g.b_sn == 1);
+  if (ak && bn) gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(g, partial, klen);
+  else if (ak && !bn) gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(g, partial, klen);
+  else if (!ak && bn) gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(g, partial, klen);
+  else gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(g, partial, klen);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  if (splits > 1) {
+    const long long total = (long long)g.M * g.N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g, partial, splits);
+    MRG_CUDA_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace mrg

@@ -1,0 +1,116 @@
+// Small streamed kernels: weight packing (gate interleave), bias-gradient column sums, Philox mask.
+#include <stdarg.h>
+
+#include "mrg_common.cuh"
+
+namespace mrg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// w_pack[d][j*4+g][i] = w_ih[d][g*H+j][i];  bias_pack[d][j*4+g] = b_ih[g*H+j] + b_hh[g*H+j]
+struct PackArgs {
+  const float* w_ih[2];
+  const float* b_ih[2];
+  const float* b_hh[2];
+};
+
+__global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __restrict__ bias_pack, int I,
+                            int H) {
+  const int d = blockIdx.y;
+  const int row = blockIdx.x;  // packed row j*4+g
+  const int j = row >> 2, g = row & 3;
+  const float* src = p.w_ih[d] + (size_t)(g * H + j) * I;
+  float* dst = w_pack + ((size_t)d * 4 * H + row) * I;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x == 0 && bias_pack != nullptr) {
+    float b = 0.f;
+    if (p.b_ih[d]) b += p.b_ih[d][g * H + j];
+    if (p.b_hh[d]) b += p.b_hh[d][g * H + j];
+    bias_pack[(size_t)d * 4 * H + row] = b;
+  }
+}
+
+int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, int I, int H, int D,
+                 cudaStream_t stream) {
+  PackArgs p;
+  for (int d = 0; d < 2; ++d) {
+    p.w_ih[d] = d < D ? w[d].w_ih : nullptr;
+    p.b_ih[d] = d < D ? w[d].b_ih : nullptr;
+    p.b_hh[d] = d < D ? w[d].b_hh : nullptr;
+  }
+  dim3 grid(4 * H, D);
+  pack_kernel<<<grid, 128, 0, stream>>>(p, w_pack, bias_pack, I, H);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// db[g*H+j] (+)= sum_b part[b][j][g]
+__global__ void colsum_kernel(const float* __restrict__ part, float* __restrict__ db, int B, int H,
+                              int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;  // interleaved column j*4+g
+  if (n >= 4 * H) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += part[(size_t)b * 4 * H + n];
+  const int j = n >> 2, g = n & 3;
+  float* o = db + g * H + j;
+  *o = accumulate ? *o + s : s;
+}
+
+int colsum_deinterleave(const float* part, float* db, int B, int H, int accumulate,
+                        cudaStream_t stream) {
+  colsum_kernel<<<(4 * H + 127) / 128, 128, 0, stream>>>(part, db, B, H, accumulate);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) — must match oracle/philox.py bit for bit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t philox4x32_10_first(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                         uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return c0;
+}
+
+__global__ void philox_mask_kernel(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared,
+                                   uint8_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * B) return;
+  const int t = idx / B, b = idx % B;
+  const uint64_t pos = offset + (uint64_t)t;
+  const uint32_t r = philox4x32_10_first((uint32_t)pos, (uint32_t)(pos >> 32), shared ? 0u : (uint32_t)b,
+                                         0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u = (float)(r >> 8) * 5.9604644775390625e-08f;  // 2^-24
+  out[idx] = u < prob ? 1 : 0;
+}
+
+}  // namespace mrg
+
+extern "C" int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared,
+                               uint8_t* out, void* stream) {
+  MRG_REQUIRE(T >= 0 && B >= 0 && out != nullptr, "mrg_philox_mask: bad arguments");
+  if (T * B == 0) return 0;
+  mrg::philox_mask_kernel<<<(T * B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, offset, prob, T, B,
+                                                                                shared, out);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mrg_version(void) { return MRG_VERSION; }
+extern "C" const char* mrg_last_error_string(void) { return mrg::last_error(); }

@@ -1,0 +1,216 @@
+"""``B200LSTM`` — the drop-in for ``torch.nn.LSTM`` at the reference's three seams.
+
+Reference call sites (all ``batch_first=True``, ``proj_size=0``, fp32):
+  mr_gen/model/utils/lstm_block.py:21,41     LSTMModule.lstm_module
+  mr_gen/model/utils/lstm_sampler.py:16,29   LSTMSampler.sampler
+  mr_gen/model/utils/mixer_block.py:237,251  LSTMMixer.mixer
+
+The class keeps ``nn.LSTM``'s constructor, parameter names / shapes / init order (so ``state_dict``s
+and seeded initialisations are interchangeable, torch/nn/modules/rnn.py:935-956, 308-311) and replaces
+the arithmetic: ``forward`` queues the hand-written sm_100a kernels through the C-ABI in
+``include/mrg_lstm.h``.  There is no cuDNN call and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _cabi
+
+_WORKSPACES = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _default_flags() -> int:
+    f = 0
+    if os.environ.get("MRG_GENERIC_REC", "0") == "1":
+        f |= _cabi.F_GENERIC_REC
+    if os.environ.get("MRG_SIMT_GEMM", "0") == "1":
+        f |= _cabi.F_SIMT_GEMM
+    return f
+
+
+class _LSTMLayerFn(torch.autograd.Function):
+    """One nn.LSTM layer (1 or 2 directions), time-major, through the C-ABI."""
+
+    @staticmethod
+    def forward(ctx, x, h0, c0, D, H, flags, *weights):
+        # weights: per direction (w_ih, w_hh, b_ih | None, b_hh | None)
+        L = _cabi.lib()
+        if not x.is_cuda:
+            raise RuntimeError("B200LSTM has no CPU path: inputs must live on a B200 (sm_100a) device")
+        if x.dtype != torch.float32:
+            raise TypeError(f"B200LSTM computes in fp32; got {x.dtype}")
+        x = x.contiguous()
+        T, B, I = x.shape
+        dev = x.device
+        need_grad = any(ctx.needs_input_grad)
+        opts = dict(dtype=torch.float32, device=dev)
+        gates = torch.empty((D, T, B, H, 4), **opts)
+        y_ext = torch.empty((D, T + 1, B, H), **opts)
+        c_ext = torch.empty((D, T + 1, B, H), **opts)
+        w_pack = torch.empty((D, 4 * H, I), **opts)
+        nbytes = L.mrg_lstm_workspace_bytes(T, B, I, H, D)
+        ws = _workspace(dev, nbytes)
+        dw = (_cabi.DirWeights * D)()
+        keep = []
+        for d in range(D):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+            for t in (w_ih, w_hh, b_ih, b_hh):
+                if t is not None and (not t.is_contiguous() or t.dtype != torch.float32 or t.device != dev):
+                    raise ValueError("B200LSTM weights must be contiguous fp32 tensors on the input's device")
+            h0d = None if h0 is None else h0[d].contiguous()
+            c0d = None if c0 is None else c0[d].contiguous()
+            keep += [h0d, c0d]
+            dw[d] = _cabi.DirWeights(_cabi.ptr(w_ih), _cabi.ptr(w_hh), _cabi.ptr(b_ih), _cabi.ptr(b_hh),
+                                     _cabi.ptr(h0d), _cabi.ptr(c0d))
+        fl = flags | (_cabi.F_TRAIN if need_grad else 0)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            st = L.mrg_lstm_layer_forward(x.data_ptr(), dw, w_pack.data_ptr(), gates.data_ptr(),
+                                          y_ext.data_ptr(), c_ext.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          T, B, I, H, D, fl, stream)
+        _cabi.check(st, "mrg_lstm_layer_forward")
+        if D == 1:
+            y = y_ext[0, 1:]
+            h_n = y_ext[:, T]
+            c_n = c_ext[:, T]
+        else:
+            y = torch.cat([y_ext[0, 1:], y_ext[1, :T]], dim=-1)
+            h_n = torch.stack([y_ext[0, T], y_ext[1, 0]])
+            c_n = torch.stack([c_ext[0, T], c_ext[1, 0]])
+        if need_grad:
+            ctx.saved = (x, gates, y_ext, c_ext, w_pack, weights, h0 is not None, c0 is not None)
+            ctx.dims = (T, B, I, H, D, flags)
+            ctx.consumed = False
+        return y, h_n, c_n
+
+    @staticmethod
+    def backward(ctx, dy, dh_n, dc_n):
+        if ctx.consumed:
+            raise RuntimeError("B200LSTM backward ran twice on the same graph: the reserve (gates) is "
+                               "overwritten in place by d(pre-activations); retain_graph is not supported")
+        ctx.consumed = True
+        L = _cabi.lib()
+        x, gates, y_ext, c_ext, w_pack, weights, has_h0, has_c0 = ctx.saved
+        T, B, I, H, D, flags = ctx.dims
+        dev = x.device
+        opts = dict(dtype=torch.float32, device=dev)
+        dy = None if dy is None else dy.contiguous()
+        dh_n = None if dh_n is None else dh_n.contiguous()
+        dc_n = None if dc_n is None else dc_n.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dh0 = torch.empty((D, B, H), **opts) if has_h0 and ctx.needs_input_grad[1] else None
+        dc0 = torch.empty((D, B, H), **opts) if has_c0 and ctx.needs_input_grad[2] else None
+        dw = (_cabi.DirWeights * D)()
+        dg = (_cabi.DirGrads * D)()
+        grads = []
+        for d in range(D):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+            dw[d] = _cabi.DirWeights(_cabi.ptr(w_ih), _cabi.ptr(w_hh), _cabi.ptr(b_ih), _cabi.ptr(b_hh),
+                                     None, None)
+            g_ih = torch.empty_like(w_ih)
+            g_hh = torch.empty_like(w_hh)
+            g_b = torch.empty((4 * H,), **opts) if (b_ih is not None or b_hh is not None) else None
+            dg[d] = _cabi.DirGrads(g_ih.data_ptr(), g_hh.data_ptr(), _cabi.ptr(g_b),
+                                   None if dh0 is None else dh0[d].data_ptr(),
+                                   None if dc0 is None else dc0[d].data_ptr())
+            grads += [g_ih, g_hh, g_b if b_ih is not None else None, g_b if b_hh is not None else None]
+        nbytes = L.mrg_lstm_workspace_bytes(T, B, I, H, D)
+        ws = _workspace(dev, nbytes)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            st = L.mrg_lstm_layer_backward(x.data_ptr(), dw, w_pack.data_ptr(), _cabi.ptr(dy),
+                                           _cabi.ptr(dh_n), _cabi.ptr(dc_n), gates.data_ptr(),
+                                           y_ext.data_ptr(), c_ext.data_ptr(), _cabi.ptr(dx), dg,
+                                           ws.data_ptr(), ws.numel(), T, B, I, H, D, flags, stream)
+        _cabi.check(st, "mrg_lstm_layer_backward")
+        ctx.saved = None
+        return (dx, dh0, dc0, None, None, None, *grads)
+
+
+def lstm_layer(x_tm: torch.Tensor, weights, hidden_size: int, directions: int = 1,
+               h0: Optional[torch.Tensor] = None, c0: Optional[torch.Tensor] = None,
+               flags: Optional[int] = None):
+    """Functional form: x_tm [T,B,I] time-major -> (y [T,B,D*H], h_n [D,B,H], c_n [D,B,H])."""
+    if flags is None:
+        flags = _default_flags()
+    return _LSTMLayerFn.apply(x_tm, h0, c0, directions, hidden_size, flags, *weights)
+
+
+class B200LSTM(nn.LSTM):
+    """``torch.nn.LSTM`` with its arithmetic replaced by the sm_100a kernels.
+
+    Subclassing keeps the constructor signature, parameter registration order (hence seeded init),
+    ``state_dict`` keys and ``isinstance(m, nn.LSTM)`` identical to the reference's module; ``forward``
+    and ``flatten_parameters`` (a cuDNN weight-layout call) are replaced."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.proj_size != 0:
+            raise NotImplementedError("B200LSTM: proj_size != 0 is not used by the reference and not built")
+
+    def flatten_parameters(self) -> None:  # no cuDNN weight buffer
+        return
+
+    def _layer_weights(self, layer: int):
+        out = []
+        for d in range(2 if self.bidirectional else 1):
+            sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
+            out += [getattr(self, "weight_ih" + sfx), getattr(self, "weight_hh" + sfx),
+                    getattr(self, "bias_ih" + sfx) if self.bias else None,
+                    getattr(self, "bias_hh" + sfx) if self.bias else None]
+        return out
+
+    def forward(self, input, hx=None):  # noqa: A002 - nn.LSTM's argument name
+        if isinstance(input, nn.utils.rnn.PackedSequence):
+            raise NotImplementedError("B200LSTM: PackedSequence input is not used by the reference")
+        if input.dim() not in (2, 3):
+            raise ValueError(f"LSTM: Expected input to be 2D or 3D, got {input.dim()}D instead")
+        batched = input.dim() == 3
+        if not batched:
+            input = input.unsqueeze(1 if not self.batch_first else 0)
+            if hx is not None:
+                hx = (hx[0].unsqueeze(1), hx[1].unsqueeze(1))
+        x = input.transpose(0, 1) if self.batch_first else input
+        if x.shape[-1] != self.input_size:
+            raise RuntimeError(f"input.size(-1) must be equal to input_size. Expected {self.input_size}, "
+                               f"got {x.shape[-1]}")
+        D = 2 if self.bidirectional else 1
+        Hs = self.hidden_size
+        B = x.shape[1]
+        if hx is not None:
+            h0, c0 = hx
+            want = (self.num_layers * D, B, Hs)
+            if tuple(h0.shape) != want or tuple(c0.shape) != want:
+                raise RuntimeError(f"Expected hidden size {want}, got {tuple(h0.shape)} / {tuple(c0.shape)}")
+        flags = _default_flags()
+        hs, cs = [], []
+        for layer in range(self.num_layers):
+            h0l = None if hx is None else hx[0][layer * D:(layer + 1) * D]
+            c0l = None if hx is None else hx[1][layer * D:(layer + 1) * D]
+            x, h_n, c_n = _LSTMLayerFn.apply(x, h0l, c0l, D, Hs, flags, *self._layer_weights(layer))
+            hs.append(h_n)
+            cs.append(c_n)
+            if self.dropout > 0 and self.training and layer + 1 < self.num_layers:
+                x = F.dropout(x, self.dropout, True)
+        h_n = torch.cat(hs, dim=0) if len(hs) > 1 else hs[0]
+        c_n = torch.cat(cs, dim=0) if len(cs) > 1 else cs[0]
+        out = x.transpose(0, 1) if self.batch_first else x
+        if not batched:
+            out = out.squeeze(1 if not self.batch_first else 0)
+            h_n, c_n = h_n.squeeze(1), c_n.squeeze(1)
+        return out, (h_n, c_n)

@@ -1,0 +1,150 @@
+"""GPU parity of the CUDA LSTM path (through the C-ABI) against torch.nn.LSTM on CPU.
+
+Tolerances (BASELINE.json north_star): fp32 hidden states within 1e-5 norm-relative
+PER STEP, loss / gradients within 1e-4 norm-relative.  The truth is torch.nn.LSTM in fp64 on CPU (the
+reference's own arithmetic); torch fp32 on CPU is checked alongside to show both sit in the same band."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _per_step_err(y, ref):
+    """max over t of ||y_t - ref_t||_inf / ||ref_t||_inf, y [B,T,F]."""
+    y, ref = y.double().cpu(), ref.double().cpu()
+    num = (y - ref).abs().amax(dim=(0, 2))
+    den = ref.abs().amax(dim=(0, 2)).clamp_min(1e-30)
+    return float((num / den).max())
+
+
+def _build(I, H, L, bi, seed=0):
+    from multimodalreactiongeneration_b200 import B200LSTM
+    torch.manual_seed(seed)
+    ref = torch.nn.LSTM(I, H, L, batch_first=True, bidirectional=bi).double()
+    mine = B200LSTM(I, H, L, batch_first=True, bidirectional=bi)
+    mine.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    return ref, mine.cuda()
+
+
+CASES = [
+    # I, H, L, bi, B, T, with_hx
+    (256, 256, 1, False, 64, 40, False),   # cluster kernel, headline shape (short T)
+    (256, 256, 2, False, 7, 23, True),     # ragged batch (masked rows), 2 layers, carried state
+    (128, 128, 2, False, 16, 33, True),    # sampler shape
+    (256, 128, 1, True, 5, 17, True),      # bidirectional (reference default simple_lstm block)
+    (128, 256, 1, True, 64, 12, False),    # bidirectional, both directions in one launch
+    (32, 32, 1, False, 3, 9, True),        # golden-fixture sizes -> generic kernels
+    (10, 16, 2, True, 3, 7, True),
+    (256, 256, 1, False, 130, 5, False),   # more row slices than one wave of clusters
+]
+
+
+@pytest.mark.parametrize("I,H,L,bi,B,T,with_hx", CASES)
+def test_forward_backward_parity(I, H, L, bi, B, T, with_hx):
+    ref, mine = _build(I, H, L, bi)
+    D = 2 if bi else 1
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, T, I, generator=g, dtype=torch.double)
+    hx = None
+    if with_hx:
+        hx = (torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5,
+              torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5)
+    wy = torch.randn(B, T, D * H, generator=g, dtype=torch.double)
+    wh = torch.randn(L * D, B, H, generator=g, dtype=torch.double)
+    wc = torch.randn(L * D, B, H, generator=g, dtype=torch.double)
+
+    xr = x.clone().requires_grad_(True)
+    hr = None if hx is None else tuple(t.clone().requires_grad_(True) for t in hx)
+    yr, (hnr, cnr) = ref(xr, hr)
+    ((yr * wy).sum() + (hnr * wh).sum() + (cnr * wc).sum()).backward()
+
+    xm = x.float().cuda().requires_grad_(True)
+    hm = None if hx is None else tuple(t.float().cuda().requires_grad_(True) for t in hx)
+    ym, (hnm, cnm) = mine(xm, hm)
+    ((ym * wy.float().cuda()).sum() + (hnm * wh.float().cuda()).sum() + (cnm * wc.float().cuda()).sum()).backward()
+    torch.cuda.synchronize()
+
+    assert _per_step_err(ym, yr) <= STATE_TOL
+    assert rel_err(hnm.cpu(), hnr) <= STATE_TOL
+    assert rel_err(cnm.cpu(), cnr) <= STATE_TOL
+    assert rel_l2(xm.grad.cpu(), xr.grad) <= GRAD_TOL
+    for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        assert rel_l2(pm.grad.cpu(), pr.grad) <= GRAD_TOL, name
+    if hx is not None:
+        assert rel_l2(hm[0].grad.cpu(), hr[0].grad) <= GRAD_TOL
+        assert rel_l2(hm[1].grad.cpu(), hr[1].grad) <= GRAD_TOL
+
+
+def test_long_sequence_headline_shape():
+    """B=64, T=300, I=H=256, 2 layers: the per-step bound must hold at the END of 300 steps."""
+    ref, mine = _build(256, 256, 2, False)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(64, 300, 256, generator=g, dtype=torch.double)
+    with torch.no_grad():
+        yr, _ = ref(x)
+        ym, _ = mine(x.float().cuda())
+    assert _per_step_err(ym, yr) <= STATE_TOL
+    # torch's own fp32 path sits in the same band (sanity of the tolerance itself)
+    with torch.no_grad():
+        y32, _ = ref.float()(x.float())
+    assert _per_step_err(y32, yr) <= STATE_TOL
+
+
+def test_cluster_and_generic_kernels_agree():
+    from multimodalreactiongeneration_b200 import lstm_layer, _cabi
+    torch.manual_seed(3)
+    T, B, I, H = 21, 9, 128, 128
+    x = torch.randn(T, B, I, device="cuda")
+    k = 1.0 / np.sqrt(H)
+    w = [torch.empty(4 * H, I, device="cuda").uniform_(-k, k), torch.empty(4 * H, H, device="cuda").uniform_(-k, k),
+         torch.empty(4 * H, device="cuda").uniform_(-k, k), torch.empty(4 * H, device="cuda").uniform_(-k, k)]
+    outs = []
+    for flags in (0, _cabi.F_GENERIC_REC | _cabi.F_SIMT_GEMM):
+        ws = [t.clone().requires_grad_(True) for t in w]
+        xx = x.clone().requires_grad_(True)
+        y, h, c = lstm_layer(xx, ws, H, 1, flags=flags)
+        (y.sin().sum() + c.sum()).backward()
+        outs.append((y, h, c, xx.grad, *[t.grad for t in ws]))
+    for a, b in zip(*outs):
+        assert rel_err(a, b) <= 2e-5
+
+
+def test_philox_mask_bit_exact():
+    import ctypes
+    from multimodalreactiongeneration_b200 import _cabi
+    from oracle import philox
+    L = _cabi.lib()
+    for seed, offset, prob, T, B, shared in [(1234, 0, 0.5, 37, 5, 0), (2**40 + 7, 2**33 + 5, 0.25, 11, 3, 0),
+                                             (99, 17, 0.75, 64, 4, 1), (5, 0, 0.0, 8, 2, 0), (5, 0, 1.0, 8, 2, 0)]:
+        out = torch.zeros(T * B, dtype=torch.uint8, device="cuda")
+        st = L.mrg_philox_mask(seed, offset, prob, T, B, shared, out.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+        _cabi.check(st, "mrg_philox_mask")
+        want = philox.sampling_mask(seed, offset, prob, T, B, shared=bool(shared))
+        assert np.array_equal(out.cpu().numpy().reshape(T, B).astype(bool), want)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 256), (77, 130, 45), (1024, 256, 4096), (19200, 1024, 256)])
+def test_projection_gemm(M, N, K):
+    from multimodalreactiongeneration_b200 import _cabi
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = a.double() @ b.double().T + bias.double()
+    ad, bd, biasd = a.cuda(), b.cuda(), bias.cuda()
+    c = torch.empty(M, N, device="cuda")
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for flags in (0, _cabi.F_SIMT_GEMM):
+        c.zero_()
+        st = L.mrg_gemm_nt(ad.data_ptr(), bd.data_ptr(), biasd.data_ptr(), c.data_ptr(), M, N, K,
+                           ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream().cuda_stream)
+        _cabi.check(st, "mrg_gemm_nt")
+        assert rel_err(c.cpu(), ref) <= 2e-6, flags
