@@ -4,8 +4,9 @@
 //   dh_t = dy_t + sum over the 8 source CTAs of their partial dh (slots in local smem, fixed order
 //          -> deterministic) ; gate derivatives -> dpre (written over the gates reserve + local smem)
 //   partial dh_{t-1}[b][k] = sum over this CTA's 4U gate columns of dpre * W_hh   (FFMA2, W in regs)
-//   8-lane shuffle reduce-scatter, one 16-byte DSMEM store per lane to the CTA that owns unit k,
-//   one cluster barrier.
+//   8-lane shuffle reduce-scatter, one 16-byte st.async per lane to the CTA that owns unit k; the
+//   store signals that CTA's mbarrier (complete_tx), so the per-step wait is a try_wait on the local
+//   mbarrier instead of a cluster barrier.
 // The bias gradient (sum of dpre over t) is accumulated in registers and written per batch row.
 #include "mrg_common.cuh"
 
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
   constexpr int NIT = (NITEMS + 255) / 256;           // per thread
   __shared__ __align__(16) float part_buf[2][CLB][R][U];
   __shared__ __align__(16) float dpre_s[R][NL];
+  __shared__ __align__(8) unsigned long long bars[2];  // bars[b]: bytes landed in part_buf[b]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ns = lane & 7;
@@ -40,9 +42,11 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / CLB;
   const int d = cid / slices;
-  const int row0 = (cid % slices) * R;
-  const int j0 = rank * U;
   const int T = a.T, B = a.B, D = a.D;
+  const int sl = cid % slices, base_rows = B / slices, rem_rows = B % slices;
+  const int row0 = sl * base_rows + min(sl, rem_rows);
+  const int nrows = base_rows + (sl < rem_rows ? 1 : 0);  // <= R, same split as the forward
+  const int j0 = rank * U;
 
   const float* __restrict__ W = d == 0 ? a.w_hh[0] : a.w_hh[1];
   float* gates = a.gates + (size_t)d * T * B * 4 * H;
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
     const int it = tid + i * 256;
     it_rl[i] = it / U;
     it_u[i] = it % U;
-    valid[i] = it < NITEMS && row0 + it_rl[i] < B;
+    valid[i] = it < NITEMS && it_rl[i] < nrows;
     dbacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     dc_reg[i] = 0.f;
     c_cur[i] = 0.f;
@@ -104,6 +108,16 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
   const uint32_t owner = (uint32_t)(kfirst / U);
   const int kin = kfirst % U;
   const uint32_t remote_base = map_to_cta(smem_u32(&part_buf[0][0][0][0]), owner);
+  const uint32_t remote_bar = map_to_cta(smem_u32(&bars[0]), owner);
+  // every lane of every CTA sends one float4 per chunk per step: R*U fp32 from each of the 8 sources
+  constexpr uint32_t STEP_BYTES = (uint32_t)(CLB * R * U * sizeof(float));
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init_fence();
+    if (T >= 1) mbar_arrive_expect_tx(smem_u32(&bars[1]), STEP_BYTES);  // round of iteration 0
+  }
+  uint32_t phase0 = 0, phase1 = 0;
 
   // prefetch registers for the first processed step
   float4 g4[NIT];
@@ -133,7 +147,11 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
     const int step = T - 1 - iter;
     const int t = d == 0 ? step : T - 1 - step;
     const int cur = iter & 1, nxt = cur ^ 1;
-    if (iter > 0) cluster_wait_acquire();
+    if (iter > 0) {
+      if (cur == 0) { mbar_wait(smem_u32(&bars[0]), phase0); phase0 ^= 1; }
+      else { mbar_wait(smem_u32(&bars[1]), phase1); phase1 ^= 1; }
+    }
+    if (tid == 0 && iter + 1 < T) mbar_arrive_expect_tx(smem_u32(&bars[cur]), STEP_BYTES);
 
     // ---- elementwise: dh, gate derivatives -> dpre ------------------------------------------
 #pragma unroll
@@ -170,6 +188,7 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
         for (int b = 0; b < RB; ++b) acc[kp][b] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int b = 0; b < RB; ++b) {
+        if (ch * RB + b >= nrows) continue;  // uniform: rows this cluster does not own
 #pragma unroll
         for (int mm = 0; mm < MM; ++mm) {
           const float4 dv = *reinterpret_cast<const float4*>(&dpre_s[ch * RB + b][mm * 32 + ns * 4]);
@@ -223,12 +242,13 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
       }
       const int rl = ch * RB + ob;
       const uint32_t off = (uint32_t)((((nxt * CLB + (int)rank) * R + rl) * U + kin) * sizeof(float));
-      st_cluster_v4(remote_base + off, make_float4(v4[0], v4[1], v4[2], v4[3]));
+      st_async_v4(remote_base + off, make_float4(v4[0], v4[1], v4[2], v4[3]), remote_bar + nxt * 8);
     }
-    __syncwarp();
-    cluster_arrive_release();
   }
-  if (T > 0) cluster_wait_acquire();
+  if (T > 0) {  // the last round (iteration T-1) carries dh0
+    if ((T & 1) == 0) mbar_wait(smem_u32(&bars[0]), phase0);
+    else mbar_wait(smem_u32(&bars[1]), phase1);
+  }
 
   // ---- dh0 / dc0 / bias-gradient partials -----------------------------------------------------
   const int fin = T & 1;
@@ -268,12 +288,11 @@ static int launch_bwd(const RecBwdArgs& a, int slices, cudaStream_t stream) {
   return 0;
 }
 
-int pick_nch(int H, int B, int D);
+void pick_partition(int H, int B, int D, int* slices_out, int* nch_out);
 
 int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream) {
-  const int nch = pick_nch(a.H, a.B, a.D);
-  const int RB = a.H == 256 ? BwdCfg<256>::RB : BwdCfg<128>::RB;
-  const int slices = (a.B + RB * nch - 1) / (RB * nch);
+  int slices, nch;
+  pick_partition(a.H, a.B, a.D, &slices, &nch);
   if (a.H == 256) {
     if (nch == 1) return launch_bwd<256, 1>(a, slices, stream);
     if (nch == 2) return launch_bwd<256, 2>(a, slices, stream);

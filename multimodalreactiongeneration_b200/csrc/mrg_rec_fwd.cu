@@ -5,7 +5,10 @@
 // every CTA's shared memory, and each step is
 //   h_{t-1} (smem) x W_hh slice (regs) -> partial sums (FFMA2) -> 16-lane shuffle reduce-scatter
 //   -> + x-projection (prefetched one step ahead) -> sigmoid/tanh gates, cell update
-//   -> h_t broadcast to the 8 CTAs through distributed shared memory -> one cluster barrier.
+//   -> h_t broadcast to the 8 CTAs through distributed shared memory with st.async: every remote
+//      store signals the destination CTA's mbarrier (complete_tx), so the only per-step wait is a
+//      warp-local try_wait on the CTA's own mbarrier — no cluster barrier, no block barrier, and the
+//      global stores of y / c / gates carry no fence.
 #include "mrg_common.cuh"
 
 namespace mrg {
@@ -28,6 +31,7 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
   constexpr int U = Cfg::U, UPT = Cfg::UPT, RB = Cfg::RB, MK = Cfg::MK, NA = Cfg::NA;
   constexpr int R = RB * NCH;
   __shared__ __align__(16) float h_buf[2][R][H];
+  __shared__ __align__(8) unsigned long long bars[2];  // bars[b]: bytes landed in h_buf[b]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ks = lane & 15;
@@ -35,9 +39,12 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / CL;
   const int d = cid / slices;
-  const int row0 = (cid % slices) * R;
-  const int j0 = rank * U;
   const int T = a.T, B = a.B;
+  // uneven row split: the first (B % slices) clusters take one row more
+  const int sl = cid % slices, base_rows = B / slices, rem_rows = B % slices;
+  const int row0 = sl * base_rows + min(sl, rem_rows);
+  const int nrows = base_rows + (sl < rem_rows ? 1 : 0);  // <= R
+  const int j0 = rank * U;
 
   const float* __restrict__ W = d == 0 ? a.w_hh[0] : a.w_hh[1];
   float* gates = a.gates + (size_t)d * T * B * 4 * H;
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
   const int init_slot = d == 0 ? 0 : T;
   for (int idx = tid; idx < R * H; idx += 256) {
     const int rl = idx / H, k = idx % H;
-    const float v = (row0 + rl < B) ? y_ext[((size_t)init_slot * B + row0 + rl) * H + k] : 0.f;
+    const float v = (rl < nrows) ? y_ext[((size_t)init_slot * B + row0 + rl) * H + k] : 0.f;
     h_buf[0][rl][k] = v;
     h_buf[1][rl][k] = 0.f;
   }
@@ -76,16 +83,29 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int row = row0 + ch * RB + ob;
-    valid[ch] = is_owner && row < B;
+    valid[ch] = is_owner && ch * RB + ob < nrows;
     c_reg[ch] = valid[ch] ? c_ext[((size_t)init_slot * B + row) * H + j] : 0.f;
     xg[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  uint32_t remote[CL];
+  uint32_t remote[CL], remote_bar[CL];
   {
     const uint32_t base = smem_u32(&h_buf[0][0][0]);
+    const uint32_t bbase = smem_u32(&bars[0]);
 #pragma unroll
-    for (int r = 0; r < CL; ++r) remote[r] = map_to_cta(base, (uint32_t)r);
+    for (int r = 0; r < CL; ++r) {
+      remote[r] = map_to_cta(base, (uint32_t)r);
+      remote_bar[r] = map_to_cta(bbase, (uint32_t)r);
+    }
   }
+  // bytes every CTA receives per step: one fp32 per (valid row of the slice, hidden unit)
+  const uint32_t step_bytes = (uint32_t)(nrows * H * sizeof(float));
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init_fence();
+    if (T >= 2) mbar_arrive_expect_tx(smem_u32(&bars[1]), step_bytes);  // round of step 0
+  }
+  uint32_t phase0 = 0, phase1 = 0;
   if (T > 0) {
     const int t0 = d == 0 ? 0 : T - 1;
 #pragma unroll
@@ -112,7 +132,13 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
             gates + (((size_t)tn * B + row0 + ch * RB + ob) * H + j) * 4));
       }
     }
-    if (step > 0) cluster_wait_acquire();  // h_buf[cur] holds h_{t-1} of all 8 CTAs
+    if (step > 0) {  // h_buf[cur] holds h_{t-1} of all 8 CTAs once its mbarrier phase completes
+      if (cur == 0) { mbar_wait(smem_u32(&bars[0]), phase0); phase0 ^= 1; }
+      else { mbar_wait(smem_u32(&bars[1]), phase1); phase1 ^= 1; }
+    }
+    // re-arm this buffer's barrier for the round of step+1 (which writes h_buf[cur] again)
+    if (tid == 0 && step + 2 < T) mbar_arrive_expect_tx(smem_u32(&bars[cur]), step_bytes);
+    const bool send = step + 1 < T;  // nobody consumes the last step's h through smem
 
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -123,6 +149,7 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
         for (int b = 0; b < RB; ++b) acc[n][b] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int b = 0; b < RB; ++b) {
+        if (ch * RB + b >= nrows) continue;  // uniform: rows this cluster does not own
         const float* hrow = &h_buf[cur][ch * RB + b][ks * 4];
 #pragma unroll
         for (int m = 0; m < MK; ++m) {
@@ -186,9 +213,11 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
         const float c = gf * c_reg[ch] + gi * gg;
         const float h = go * tanhf(c);
         c_reg[ch] = c;
-        const uint32_t off = (uint32_t)(((nxt * R + rl) * H + j) * sizeof(float));
+        if (send) {
+          const uint32_t off = (uint32_t)(((nxt * R + rl) * H + j) * sizeof(float));
 #pragma unroll
-        for (int r = 0; r < CL; ++r) st_cluster_f32(remote[r] + off, h);
+          for (int r = 0; r < CL; ++r) st_async_f32(remote[r] + off, h, remote_bar[r] + nxt * 8);
+        }
         y_ext[((size_t)out_slot * B + row) * H + j] = h;
         c_ext[((size_t)out_slot * B + row) * H + j] = c;
         if (a.train)
@@ -196,12 +225,11 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
               make_float4(gi, gf, gg, go);
       }
     }
-    __syncwarp();
-    cluster_arrive_release();
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) xg[ch] = xg_n[ch];
   }
-  if (T > 0) cluster_wait_acquire();  // nobody exits while peers may still write into its smem
+  // Exit safety: the last round of remote stores into this CTA (step T-2) was waited for at step
+  // T-1, and nobody sends at step T-1, so no store can target the shared memory of an exited CTA.
 }
 
 template <int H, int NCH>
@@ -251,22 +279,30 @@ int max_active_clusters(int H) {
 
 bool rec_cluster_supported(int H) { return H == 128 || H == 256; }
 
-// rows per cluster = RB * NCH; pick the smallest NCH in {1,2,4} whose cluster count fits one wave
-int pick_nch(int H, int B, int D) {
+// Partition of the batch: `slices` clusters per direction, rows split as evenly as possible, and
+// NCH register chunks of RB rows per cluster.  One wave of co-resident clusters whenever B allows.
+void pick_partition(int H, int B, int D, int* slices_out, int* nch_out) {
   const int RB = H == 256 ? FwdCfg<256>::RB : FwdCfg<128>::RB;
   int maxc = max_active_clusters(H);
-  if (maxc <= 0) maxc = 16;
-  for (int nch = 1; nch <= 4; nch *= 2) {
-    const int slices = (B + RB * nch - 1) / (RB * nch);
-    if (D * slices <= maxc) return nch;
+  if (maxc <= 0) maxc = 15;
+  int per_dir = maxc / D;
+  if (per_dir < 1) per_dir = 1;
+  int slices = (B + RB - 1) / RB;            // one chunk per cluster if they all fit
+  if (slices > per_dir) slices = per_dir;     // otherwise use every cluster slot and add chunks
+  int rows = (B + slices - 1) / slices;
+  int nch = (rows + RB - 1) / RB;
+  if (nch > 4) {                              // more rows than 4 chunks hold: several waves
+    nch = 4;
+    slices = (B + 4 * RB - 1) / (4 * RB);
   }
-  return 4;
+  if (nch == 3) nch = 4;
+  *slices_out = slices;
+  *nch_out = nch;
 }
 
 int rec_forward_cluster(const RecArgs& a, cudaStream_t stream) {
-  const int nch = pick_nch(a.H, a.B, a.D);
-  const int RB = a.H == 256 ? FwdCfg<256>::RB : FwdCfg<128>::RB;
-  const int slices = (a.B + RB * nch - 1) / (RB * nch);
+  int slices, nch;
+  pick_partition(a.H, a.B, a.D, &slices, &nch);
   if (a.H == 256) {
     if (nch == 1) return launch_fwd<256, 1>(a, slices, stream);
     if (nch == 2) return launch_fwd<256, 2>(a, slices, stream);

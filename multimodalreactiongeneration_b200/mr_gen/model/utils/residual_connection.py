@@ -1,0 +1,29 @@
+"""Mirror of mr_gen/model/utils/residual_connection.py:5-37 (``y = Dropout(LN(module(x) + x))``)."""
+from torch import nn
+
+
+class ResidualConnection(nn.Module):
+    """Wraps ``module``; extra tuple outputs (LSTM states) pass through untouched.
+
+    The reference derives from ``pl.LightningModule`` only as a base class; ``nn.Module`` gives the
+    same parameters and ``state_dict`` keys (``module.*``, ``layer_norm.*``)."""
+
+    def __init__(self, module: nn.Module, use_layer_norm=True, num_nodes: int = -1, dropout=0.0):
+        super().__init__()
+        if use_layer_norm and num_nodes == -1:
+            raise ValueError("num_nodes must be specified when use_layer_norm is set to True.")
+        self.module = module
+        self.use_layer_norm = use_layer_norm
+        self.layer_norm = nn.LayerNorm(num_nodes) if use_layer_norm else None
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x, *args, **kwargs):
+        out = self.module(x, *args, **kwargs)
+        extras = None
+        if isinstance(out, (tuple, list)):
+            out, extras = out[0], tuple(out[1:])
+        out = out + x
+        if self.layer_norm is not None:
+            out = self.layer_norm(out)
+        out = self.dropout(out)
+        return out if extras is None else (out, *extras)

@@ -16,6 +16,12 @@ def timeit(fn, n=10, warm=3):
     return ts[len(ts)//2]
 
 def main():
+    import ctypes
+    from multimodalreactiongeneration_b200 import _cabi
+    L = _cabi.lib()
+    v = [ctypes.c_int() for _ in range(5)]
+    L.mrg_device_info(*[ctypes.byref(x) for x in v])
+    print("sm_count, max_clusters_h256, max_clusters_h128, cc =", [x.value for x in v], flush=True)
     for (B, T, I, H, L, bi) in [(64, 300, 256, 256, 1, False), (64, 300, 256, 256, 2, False), (64, 300, 128, 128, 2, False),
                                 (256, 300, 256, 256, 1, False), (64, 300, 256, 128, 1, True), (8, 300, 256, 256, 1, False)]:
         m = B200LSTM(I, H, L, batch_first=True, bidirectional=bi).cuda()
