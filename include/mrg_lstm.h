@@ -104,6 +104,13 @@ int mrg_gemm_nt(const float* a, const float* b, const float* bias, float* c, int
 int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared, uint8_t* out,
                     void* stream);
 
+/* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded,
+ * and CUDA-event timing of the recurrent / GEMM launches on their own stream.  mrg_profile_read fills
+ * ms[3], n[3] for {recurrent forward, recurrent backward, GEMM} and resets the record. */
+unsigned long long mrg_launch_count(void);
+int mrg_profile_enable(int on);
+int mrg_profile_read(float* ms, int* n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE = 1, 2, 4, 8
 EXPORTS = (
     "mrg_version", "mrg_last_error_string", "mrg_device_info", "mrg_lstm_workspace_bytes",
     "mrg_lstm_layer_forward", "mrg_lstm_layer_backward", "mrg_gemm_nt", "mrg_philox_mask",
+    "mrg_launch_count", "mrg_profile_enable", "mrg_profile_read",
 )
 
 
@@ -63,8 +64,27 @@ def lib() -> ctypes.CDLL:
     L.mrg_gemm_nt.restype = c_int
     L.mrg_philox_mask.argtypes = [c_uint64, c_uint64, c_float, c_int, c_int, c_int, c_void_p, c_void_p]
     L.mrg_philox_mask.restype = c_int
+    L.mrg_launch_count.restype = ctypes.c_ulonglong
+    L.mrg_profile_enable.argtypes = [c_int]
+    L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
     _LIB = L
     return L
+
+
+def launch_count() -> int:
+    return int(lib().mrg_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    lib().mrg_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> {"rec_fwd": (ms, n), "rec_bwd": (ms, n), "gemm": (ms, n)} since profile_enable(True)."""
+    ms = (c_float * 3)()
+    n = (c_int * 3)()
+    check(lib().mrg_profile_read(ms, n), "mrg_profile_read")
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("rec_fwd", "rec_bwd", "gemm"))}
 
 
 def check(status: int, what: str) -> None:

@@ -173,4 +173,14 @@ int colsum_deinterleave(const float* part, float* db, int B, int H, int accumula
                         cudaStream_t stream);
 int max_active_clusters(int H);
 
+// launch accounting / live kernel timing (bench.py's gpu_launches and roofline numbers)
+void count_launch(int n = 1);
+struct ProfScope {  // brackets a launch with CUDA events on its stream when profiling is enabled
+  ProfScope(int kind, cudaStream_t stream);
+  ~ProfScope();
+  int slot;
+  cudaStream_t stream;
+};
+enum { PROF_REC_FWD = 0, PROF_REC_BWD = 1, PROF_GEMM = 2, PROF_KINDS = 3 };
+
 }  // namespace mrg

@@ -137,6 +137,8 @@ int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaSt
   klen = (klen + BK - 1) / BK * BK;
   if (klen == 0) klen = BK;
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
+  ProfScope prof(PROF_GEMM, stream);
+  count_launch(splits > 1 ? 2 : 1);
   const bool ak = (g.a_sk == 1), bn = (g.b_sn == 1);
   if (ak && bn) gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(g, partial, klen);
   else if (ak && !bn) gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(g, partial, klen);

@@ -15,6 +15,33 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+// ---------------------------------------------------------------------------------------------
+// launch counter + event-timed launches
+// ---------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+static int g_prof_on = 0;
+constexpr int PROF_MAX = 8192;
+static cudaEvent_t g_ev[PROF_MAX][2];
+static int g_ev_kind[PROF_MAX];
+static int g_ev_created = 0, g_ev_used = 0;
+
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+ProfScope::ProfScope(int kind, cudaStream_t st) : slot(-1), stream(st) {
+  if (!g_prof_on || g_ev_used >= PROF_MAX) return;
+  slot = g_ev_used++;
+  if (slot >= g_ev_created) {
+    cudaEventCreate(&g_ev[slot][0]);
+    cudaEventCreate(&g_ev[slot][1]);
+    g_ev_created = slot + 1;
+  }
+  g_ev_kind[slot] = kind;
+  cudaEventRecord(g_ev[slot][0], stream);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_ev[slot][1], stream);
+}
+
 // w_pack[d][j*4+g][i] = w_ih[d][g*H+j][i];  bias_pack[d][j*4+g] = b_ih[g*H+j] + b_hh[g*H+j]
 struct PackArgs {
   const float* w_ih[2];
@@ -49,6 +76,7 @@ int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack,
   dim3 grid(4 * H, D);
   pack_kernel<<<grid, 128, 0, stream>>>(p, w_pack, bias_pack, I, H);
   MRG_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -68,6 +96,7 @@ int colsum_deinterleave(const float* part, float* db, int B, int H, int accumula
                         cudaStream_t stream) {
   colsum_kernel<<<(4 * H + 127) / 128, 128, 0, stream>>>(part, db, B, H, accumulate);
   MRG_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -109,6 +138,30 @@ extern "C" int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T
   mrg::philox_mask_kernel<<<(T * B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, offset, prob, T, B,
                                                                                 shared, out);
   MRG_CUDA_CHECK(cudaGetLastError());
+  mrg::count_launch();
+  return 0;
+}
+
+extern "C" unsigned long long mrg_launch_count(void) { return mrg::g_launches; }
+
+extern "C" int mrg_profile_enable(int on) {
+  mrg::g_prof_on = on ? 1 : 0;
+  if (on) mrg::g_ev_used = 0;
+  return 0;
+}
+
+// Sums the event-timed durations recorded since mrg_profile_enable(1): ms[k], n[k] for k in
+// {0: recurrent forward, 1: recurrent backward, 2: GEMM}.  Synchronises on the recorded events.
+extern "C" int mrg_profile_read(float* ms, int* n) {
+  for (int k = 0; k < mrg::PROF_KINDS; ++k) { ms[k] = 0.f; n[k] = 0; }
+  for (int i = 0; i < mrg::g_ev_used; ++i) {
+    MRG_CUDA_CHECK(cudaEventSynchronize(mrg::g_ev[i][1]));
+    float t = 0.f;
+    MRG_CUDA_CHECK(cudaEventElapsedTime(&t, mrg::g_ev[i][0], mrg::g_ev[i][1]));
+    ms[mrg::g_ev_kind[i]] += t;
+    n[mrg::g_ev_kind[i]] += 1;
+  }
+  mrg::g_ev_used = 0;
   return 0;
 }
 

@@ -284,6 +284,8 @@ static int launch_bwd(const RecBwdArgs& a, int slices, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  ProfScope prof(PROF_REC_BWD, stream);
+  count_launch();
   MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_bwd_cluster_kernel<H, NCH>, a, slices));
   return 0;
 }

@@ -170,6 +170,8 @@ int rec_forward_generic(const RecArgs& a, cudaStream_t stream) {
     MRG_CUDA_CHECK(cudaFuncSetAttribute(rec_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
   const int slices = (a.B + GR - 1) / GR;
+  ProfScope prof(PROF_REC_FWD, stream);
+  count_launch();
   rec_fwd_generic_kernel<<<a.D * slices, 256, smem, stream>>>(a);
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -182,6 +184,8 @@ int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream) {
     MRG_CUDA_CHECK(cudaFuncSetAttribute(rec_bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
   const int slices = (a.B + GR - 1) / GR;
+  ProfScope prof(PROF_REC_BWD, stream);
+  count_launch();
   rec_bwd_generic_kernel<<<a.D * slices, 256, smem, stream>>>(a);
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -1,0 +1,140 @@
+"""Lightning-free training runtime for the LSTM models (reference: mr_gen/model/<m>/trainer.py and the
+work-in-progress mr_gen/tainer/trainer.py — hydra main -> ``pl.Trainer(strategy="ddp").fit``).
+
+What Lightning did for the reference and what replaces it here:
+  * one process per GPU + DDP gradient averaging  -> ``FlatGradBucket``: every ``param.grad`` is a view
+    into ONE flat fp32 buffer, so autograd accumulates straight into it and a single
+    ``all_reduce`` (NCCL over NVLink on GPU boxes, gloo in the CPU tests) averages all gradients;
+  * ``training_step`` / ``configure_optimizers`` hooks -> called directly (same names on the models);
+  * ModelCheckpoint -> ``save_checkpoint`` / ``load_checkpoint`` writing ``{"state_dict": ...}`` with the
+    reference's keys (mr_gen/model/model_loader.py:23-24 reads exactly that).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class FlatGradBucket:
+    """All gradients of ``module`` in one contiguous fp32 buffer (the only collective of the path)."""
+
+    def __init__(self, module: nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / dist.get_world_size())
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+
+def broadcast_parameters(module: nn.Module, src: int = 0) -> None:
+    """DDP's constructor broadcast: every rank starts from rank ``src``'s weights."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
+
+
+def build_optimizer(model: nn.Module):
+    """``configure_optimizers`` of the reference models returns {"optimizer", "lr_scheduler": {...}}."""
+    cfg = model.configure_optimizers()
+    sched = cfg.get("lr_scheduler", {}).get("scheduler") if isinstance(cfg, dict) else None
+    return cfg["optimizer"], sched
+
+
+class Trainer:
+    """fit loop: zero bucket -> training_step -> backward -> one all-reduce -> optimizer step."""
+
+    def __init__(self, model: nn.Module, max_epochs: int = 1, log_every: int = 0,
+                 ckpt_dir: Optional[str] = None):
+        self.model = model
+        self.max_epochs = max_epochs
+        self.log_every = log_every
+        self.ckpt_dir = ckpt_dir
+        broadcast_parameters(model)
+        # the bucket must own the .grad tensors before the optimizer is created
+        self.bucket = FlatGradBucket(model)
+        self.optimizer, self.scheduler = build_optimizer(model)
+        self.global_step = 0
+
+    def train_step(self, batch) -> torch.Tensor:
+        self.bucket.zero()
+        loss = self.model.training_step(batch)["loss"]
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        self.optimizer.step()
+        self.global_step += 1
+        return loss.detach()
+
+    @torch.no_grad()
+    def validate(self, batches: Iterable) -> float:
+        self.model.eval()
+        losses = [float(self.model.validation_step(b)["loss"]) for b in batches]
+        self.model.train()
+        return sum(losses) / max(1, len(losses))
+
+    def fit(self, train_batches: Callable[[int], Iterable], val_batches: Optional[Callable[[int], Iterable]] = None):
+        history = []
+        for epoch in range(self.max_epochs):
+            self.model.current_epoch = epoch
+            last = None
+            for batch in train_batches(epoch):
+                last = self.train_step(batch)
+                if self.log_every and self.global_step % self.log_every == 0 and _rank() == 0:
+                    print(f"epoch {epoch} step {self.global_step} train_loss {float(last):.6f}", flush=True)
+            if self.scheduler is not None:
+                self.scheduler.step()
+            rec = {"epoch": epoch, "train_loss": None if last is None else float(last)}
+            if val_batches is not None:
+                rec["val_loss"] = self.validate(val_batches(epoch))
+            history.append(rec)
+            if self.ckpt_dir and _rank() == 0:
+                save_checkpoint(self.model, os.path.join(self.ckpt_dir, "last.ckpt"), epoch, self.global_step)
+        return history
+
+
+def _rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def save_checkpoint(model: nn.Module, path: str, epoch: int = 0, global_step: int = 0) -> None:
+    """Lightning-shaped ``.ckpt``: a dict whose ``"state_dict"`` has the reference's keys."""
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+                "epoch": epoch, "global_step": global_step}, path)
+
+
+def load_checkpoint(model: nn.Module, path: str, map_location="cpu") -> Dict:
+    ckpt = torch.load(path, map_location=map_location)
+    model.load_state_dict(ckpt["state_dict"])
+    return ckpt
+
+
+def init_distributed(backend: Optional[str] = None) -> int:
+    """One process per GPU, rendezvous from the torchrun environment."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend=backend)
+    return world
