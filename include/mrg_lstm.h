@@ -99,6 +99,15 @@ int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weights* w, const
 int mrg_gemm_nt(const float* a, const float* b, const float* bias, float* c, int M, int N, int K,
                 void* workspace, size_t workspace_bytes, int flags, void* stream);
 
+/* General strided form used by the backward (and by the tests): A(m,k) = a[m*a_sm + k*a_sk],
+ * B(k,n) = b[k*b_sk + n*b_sn], C[row(m)][n] (+)= sum_k A*B (+ bias[n]); row(m) = (m%4)*deint_H + m/4 when
+ * deint_H > 0 (gate de-interleave of weight gradients), else m. */
+int mrg_gemm_strided(const float* a, long long a_sm, long long a_sk, const float* b, long long b_sk,
+                     long long b_sn, const float* bias, float* c, long long ldc, int M, int N, int K,
+                     int accumulate, int deint_H, void* workspace, size_t workspace_bytes, int flags,
+                     void* stream);
+size_t mrg_gemm_workspace_bytes(int M, int N, int K);
+
 /* Scheduled-sampling mask: out[t*B+b] = philox4x32_10(ctr=(lo(offset+t), hi(offset+t), shared?0:b, 0),
  * key=(lo(seed), hi(seed)))[0] >> 8 as a 24-bit uniform < prob.  out is a DEVICE uint8 buffer. */
 int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared, uint8_t* out,

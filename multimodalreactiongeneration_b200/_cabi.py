@@ -13,7 +13,8 @@ F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE = 1, 2, 4, 8
 EXPORTS = (
     "mrg_version", "mrg_last_error_string", "mrg_device_info", "mrg_lstm_workspace_bytes",
     "mrg_lstm_layer_forward", "mrg_lstm_layer_backward", "mrg_gemm_nt", "mrg_philox_mask",
-    "mrg_launch_count", "mrg_profile_enable", "mrg_profile_read",
+    "mrg_launch_count", "mrg_profile_enable", "mrg_profile_read", "mrg_gemm_strided",
+    "mrg_gemm_workspace_bytes",
 )
 
 
@@ -64,6 +65,12 @@ def lib() -> ctypes.CDLL:
     L.mrg_gemm_nt.restype = c_int
     L.mrg_philox_mask.argtypes = [c_uint64, c_uint64, c_float, c_int, c_int, c_int, c_void_p, c_void_p]
     L.mrg_philox_mask.restype = c_int
+    LL = ctypes.c_longlong
+    L.mrg_gemm_strided.argtypes = [c_void_p, LL, LL, c_void_p, LL, LL, c_void_p, c_void_p, LL, c_int, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]
+    L.mrg_gemm_strided.restype = c_int
+    L.mrg_gemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.mrg_gemm_workspace_bytes.restype = c_size_t
     L.mrg_launch_count.restype = ctypes.c_ulonglong
     L.mrg_profile_enable.argtypes = [c_int]
     L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]

@@ -215,3 +215,20 @@ extern "C" int mrg_gemm_nt(const float* a, const float* b, const float* bias, fl
   g.M = M; g.N = N; g.K = K;
   return run_gemm(g, workspace, workspace_bytes, flags, (cudaStream_t)stream);
 }
+
+extern "C" int mrg_gemm_strided(const float* a, long long a_sm, long long a_sk, const float* b, long long b_sk,
+                                long long b_sn, const float* bias, float* c, long long ldc, int M, int N, int K,
+                                int accumulate, int deint_H, void* workspace, size_t workspace_bytes, int flags,
+                                void* stream) {
+  MRG_REQUIRE(a && b && c && M >= 0 && N >= 0 && K >= 0, "mrg_gemm_strided: bad arguments");
+  MRG_REQUIRE(check_device() == 1, "mrg_gemm_strided: this library only runs on compute capability 10.x (B200)");
+  GemmArgs g = {};
+  g.a = a; g.a_sm = a_sm; g.a_sk = a_sk;
+  g.b = b; g.b_sk = b_sk; g.b_sn = b_sn;
+  g.bias = bias; g.c = c; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K;
+  g.accumulate = accumulate; g.row_deinterleave_H = deint_H;
+  return run_gemm(g, workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+extern "C" size_t mrg_gemm_workspace_bytes(int M, int N, int K) { return gemm_ws(M, N, K) + 256; }

@@ -147,4 +147,39 @@ def test_projection_gemm(M, N, K):
         st = L.mrg_gemm_nt(ad.data_ptr(), bd.data_ptr(), biasd.data_ptr(), c.data_ptr(), M, N, K,
                            ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream().cuda_stream)
         _cabi.check(st, "mrg_gemm_nt")
-        assert rel_err(c.cpu(), ref) <= 2e-6, flags
+        assert rel_err(c.cpu(), ref) <= (5e-6 if flags == 0 else 2e-6), flags  # 3xTF32: tensor-core accumulation truncates
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,deint", [(1024, 256, 2464, 256), (300, 256, 1024, 0), (128, 128, 32, 0),
+                                         (1000, 132, 260, 0)])
+def test_strided_gemm_all_majors(a_mn, b_mn, M, N, K, deint):
+    """The tcgen05 3xTF32 GEMM against fp64 for K-major / MN-major operands (the weight-gradient GEMMs are
+    MN-major on both sides), split-K, accumulate and the gate de-interleaving epilogue."""
+    from multimodalreactiongeneration_b200 import _cabi
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    ref = A.double() @ Bm.double() + c0.double()
+    if deint:
+        H = deint
+        idx = torch.arange(M)
+        rows = (idx % 4) * H + idx // 4
+        full = torch.empty_like(ref)
+        full[rows] = A.double() @ Bm.double()
+        ref = full + c0.double()
+    a_dev = (A.t().contiguous() if a_mn else A.contiguous()).cuda()
+    b_dev = (Bm.contiguous() if b_mn else Bm.t().contiguous()).cuda()
+    a_sm, a_sk = (1, M) if a_mn else (K, 1)
+    b_sk, b_sn = (N, 1) if b_mn else (1, K)
+    ws = torch.empty(L.mrg_gemm_workspace_bytes(M, N, K), dtype=torch.uint8, device="cuda")
+    for flags in (0, _cabi.F_SIMT_GEMM):
+        c = c0.clone().cuda()
+        st = L.mrg_gemm_strided(a_dev.data_ptr(), a_sm, a_sk, b_dev.data_ptr(), b_sk, b_sn, None, c.data_ptr(),
+                                N, M, N, K, 1, deint, ws.data_ptr(), ws.numel(), flags,
+                                torch.cuda.current_stream().cuda_stream)
+        _cabi.check(st, "mrg_gemm_strided")
+        torch.cuda.synchronize()
+        assert rel_err(c.cpu(), ref) <= (5e-6 if flags == 0 else 2e-6), (flags, a_mn, b_mn)

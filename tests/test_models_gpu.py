@@ -1,0 +1,162 @@
+"""GPU parity of the mirrored model code against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py -> tests/golden/*.npz): same state_dict keys, outputs, losses and gradients."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL, GRAD_TOL = 1e-5, 1e-4
+
+
+def _cuda(sd):
+    return {k: v.cuda() for k, v in sd.items()}
+
+
+def _check_grads(model, grads, prefix=""):
+    for name, p in model.named_parameters():
+        want = grads[prefix + name]
+        assert p.grad is not None, name
+        assert rel_l2(p.grad.cpu(), want) <= GRAD_TOL, name
+
+
+def _layerd(bi):
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.lstm_block import LSTMLayerd
+    if bi:
+        return LSTMLayerd(input_size=32, lstm_hidden_size=16, affine_hidden_size=32, bottleneck_size=8,
+                          num_layers=2, num_layers_per_block=1, output_size=32, dropout=0.0, bidirectional=True,
+                          use_layer_norm=True, use_relu=True, use_mixing=True, use_residual=True)
+    return LSTMLayerd(input_size=32, lstm_hidden_size=32, affine_hidden_size=32, bottleneck_size=8,
+                      num_layers=2, num_layers_per_block=1, output_size=32, dropout=0.0, bidirectional=False,
+                      use_layer_norm=True, use_mixing=False, use_residual=True, use_feed_forward=False)
+
+
+@pytest.mark.parametrize("name,bi", [("lstm_layerd_uni", False), ("lstm_layerd_bi_mix_ffn", True)])
+def test_lstm_layerd_matches_reference(name, bi):
+    sd, ins, outs, grads, _ = load_golden(name)
+    m = _layerd(bi)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x = ins["x"].cuda().requires_grad_(True)
+    y, hxs = m(x)
+    assert hxs is None  # quirk Q2: the input states are handed back
+    (y * ins["w"].cuda()).sum().backward()
+    assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
+    assert rel_l2(x.grad.cpu(), grads["x"]) <= GRAD_TOL
+    _check_grads(m, grads)
+
+
+def test_lstm_sampler_matches_reference():
+    from multimodalreactiongeneration_b200.mr_gen.model.utils import LSTMSampler
+    sd, ins, outs, _, _ = load_golden("lstm_sampler")
+    m = LSTMSampler(16, 2, 0.0, 4)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x = ins["x"].cuda()
+    with torch.no_grad():
+        y1, hx = m(x[:, :8])
+        y2, hx2 = m(x[:, 8:], hx)
+    assert rel_err(y1.cpu(), outs["y1"]) <= OUT_TOL
+    assert rel_err(y2.cpu(), outs["y2"]) <= OUT_TOL
+    assert rel_err(hx2[0].cpu(), outs["h"]) <= OUT_TOL
+    assert rel_err(hx2[1].cpu(), outs["c"]) <= OUT_TOL
+
+
+def _lws(scheduled=False):
+    from multimodalreactiongeneration_b200.mr_gen.model.lstm_with_sampling.lstm_with_sample import LSTMwithSample
+    from multimodalreactiongeneration_b200.mr_gen.utils.config import DictConfig
+    model = DictConfig(
+        nmels=9, delta_order=0, use_centroid=True, use_angle=True, sampler_hidden_size=16,
+        sampler_num_layers=2, sampler_dropout_rate=0, sampling_rate=16000, shift=160, fps=25, pred_fps=50.0,
+        hidden_size=32, bottleneck_size=8, num_layers=2, num_lstm=1, dropout_rate=0.0, use_layer_norm=True,
+        use_relu=True, use_mixing=False, use_residual=True, delta_loss_scale=1, loss_type="huber",
+        loss_reduction="mean", huber_delta=1.0, smoothl1_beta=1.0, use_scheduled_sampling=scheduled, max_epochs=6)
+    optim = DictConfig(use_optimizer="adam", lr=5e-6, weight_decay=1e-2, use_lr_sched=True, max_epochs=100,
+                       momentum=0.9)
+    metrics = DictConfig(use_centroid=True, use_angle=True, delta_order=0)
+    return LSTMwithSample(model, optim, metrics)
+
+
+def _lws_batch(ins):
+    names = ["acoustic", "motion_p", "motion_s", "lead_a", "lead_p", "lead_s", "target"]
+    return [(ins[n].cuda(), None) for n in names]
+
+
+def test_lstm_with_sample_forward_and_teacher_forced_step():
+    sd, ins, outs, grads, meta = load_golden("lstm_with_sample")
+    m = _lws()
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    assert m.ratio == int(meta["ratio"])
+    batch = _lws_batch(ins)
+    y, (lead_len, _, _), (hx_s, hxs) = m.forward(*batch[:-1])
+    assert hxs is None and lead_len == int(meta["lead_len"])
+    assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
+    assert rel_err(hx_s[0].cpu(), outs["hs"]) <= OUT_TOL
+    assert rel_err(hx_s[1].cpu(), outs["cs"]) <= OUT_TOL
+    loss = m.training_step(batch)["loss"]
+    loss.backward()
+    assert abs(float(loss) - float(outs["loss"])) <= 1e-4 * abs(float(outs["loss"]))
+    _check_grads(m, grads)
+
+
+def test_lstm_with_sample_rollout_modes():
+    sd, ins, outs, _, _ = load_golden("lstm_with_sample")
+    m = _lws()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    batch = _lws_batch(ins)
+    with torch.no_grad():
+        tf, _ = m.prediction(batch)
+        free, _ = m.prediction(batch, full_generation=True)
+        ss, _ = m.prediction(batch, use_scheduled_sampling=True, sampling_mask=ins["mask_ss"].bool())
+    assert rel_err(tf.cpu(), outs["pred_tf"]) <= OUT_TOL
+    assert rel_err(free.cpu(), outs["pred_free"]) <= 5e-5  # 7 free-running steps compound fp32 rounding
+    assert rel_err(ss.cpu(), outs["pred_ss"]) <= 5e-5
+
+
+def test_lstm_with_sample_scheduled_sampling_training_step():
+    """Gradient through the fed-back predictions (Q6) with the reference's own mask draw (Q4)."""
+    sd, ins, outs, grads, _ = load_golden("lstm_with_sample")
+    m = _lws(scheduled=True)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.current_epoch = 3
+    torch.manual_seed(77)  # same CPU draw as the fixture: torch.rand(T) < 3/6
+    loss = m.training_step(_lws_batch(ins))["loss"]
+    loss.backward()
+    assert abs(float(loss) - float(outs["loss_ss"])) <= 1e-4 * abs(float(outs["loss_ss"]))
+    _check_grads(m, grads, prefix="ss/")
+
+
+def test_simple_lstm_matches_reference():
+    from multimodalreactiongeneration_b200.mr_gen.model.simple_lstm.simple_lstm import SimpleLSTM
+    from multimodalreactiongeneration_b200.mr_gen.utils.config import DictConfig
+    sd, ins, outs, grads, meta = load_golden("simple_lstm")
+    cfg = DictConfig(
+        acostic_feat_size=10, motion_feat_size=6, motion_num_lstm=1, acostic_num_lstm=1, acostic_num_layers=2,
+        motion_num_layers=2, acostic_lstm_size=32, motion_lstm_size=32, acostic_affine_size=32,
+        motion_affine_size=32, acostic_output_size=32, motion_output_size=32, att_heads=int(meta["heads"]),
+        att_num_layers=2, att_use_residual=True, att_use_layer_norm=True, dropout_rate=0, output_size=6,
+        bidirectional=False, use_layer_norm=True, use_relu=True, use_mixing=True, use_residual=True,
+        decoder_num_layers=2, decoder_num_lstm=1, decoder_lstm_size=32, decoder_affine_size=32,
+        decoder_bottleneck_size=8, decoder_output_size=32, decoder_mapping_size=8, decoder_bidirectional=False,
+        decoder_use_layer_norm=True, decoder_use_relu=True, decoder_use_mixing=True, decoder_use_residual=True,
+        delta_loss_scale=1, all_static=False)
+    optim = DictConfig(use_optimizer="adam", lr=5e-6, weight_decay=1e-2, use_lr_sched=True, max_epochs=100,
+                       momentum=0.9)
+    metrics = DictConfig(use_centroid=True, use_angle=True, delta_order=0)
+    m = SimpleLSTM(cfg, optim, metrics)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    a, mo, tgt = ins["acoustic"].cuda(), ins["motion"].cuda(), ins["target"].cuda()
+    y = m(a, mo)
+    assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
+    loss = m.training_step((a, mo, tgt))["loss"]
+    loss.backward()
+    assert abs(float(loss) - float(outs["loss"])) <= 1e-4 * abs(float(outs["loss"]))
+    _check_grads(m, grads)
