@@ -160,3 +160,21 @@ def test_simple_lstm_matches_reference():
     loss.backward()
     assert abs(float(loss) - float(outs["loss"])) <= 1e-4 * abs(float(outs["loss"]))
     _check_grads(m, grads)
+
+
+def test_lstm_mixer_layerd_matches_reference():
+    """lstmformer's token mixer (mixer_block.py:762-843): 2 residual LSTM blocks + single-Linear FFN."""
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.mixer_block import LSTMMixerLayerd
+    sd, ins, outs, grads, meta = load_golden("lstm_mixer_layerd")
+    m = LSTMMixerLayerd(hidden_size=32, num_layerd=2, residual=True, residual_layer_norm=True,
+                        nonlinearity="none", device=torch.device("cpu"))
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x = ins["x"].cuda().requires_grad_(True)
+    y, hx, other = m(x)
+    assert hx is None and bool(meta["hx_is_none"]) and other == (None,)  # quirk Q3
+    (y * ins["w"].cuda()).sum().backward()
+    assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
+    assert rel_l2(x.grad.cpu(), grads["x"]) <= GRAD_TOL
+    _check_grads(m, grads)
