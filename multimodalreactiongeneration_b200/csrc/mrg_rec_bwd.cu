@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
   const int cid = blockIdx.x / CLB;
   const int d = cid / slices;
   const int T = a.T, B = a.B, D = a.D;
+  const uint32_t BH = (uint32_t)B * H;
   const int sl = cid % slices, base_rows = B / slices, rem_rows = B % slices;
   const int row0 = sl * base_rows + min(sl, rem_rows);
   const int nrows = base_rows + (sl < rem_rows ? 1 : 0);  // <= R, same split as the forward
@@ -131,11 +132,10 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
       cp[i] = 0.f;
       dyv[i] = 0.f;
       if (valid[i]) {
-        const size_t row = row0 + it_rl[i];
-        const int j = j0 + it_u[i];
-        g4[i] = __ldcg(reinterpret_cast<const float4*>(gates + (((size_t)t * B + row) * H + j) * 4));
-        cp[i] = c_ext[((size_t)prev_slot * B + row) * H + j];
-        if (a.dy) dyv[i] = a.dy[((size_t)t * B + row) * D * H + (size_t)d * H + j];
+        const uint32_t rj = (uint32_t)(row0 + it_rl[i]) * H + j0 + it_u[i];
+        g4[i] = __ldcg(reinterpret_cast<const float4*>(gates) + (uint32_t)t * BH + rj);
+        cp[i] = c_ext[(uint32_t)prev_slot * BH + rj];
+        if (a.dy) dyv[i] = a.dy[((uint32_t)t * B + row0 + it_rl[i]) * (uint32_t)(D * H) + d * H + j0 + it_u[i]];
       }
     }
   };
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
 #pragma unroll
         for (int s = 0; s < CLB; ++s) dh += part_buf[cur][s][rl][u];
         const float4 g = g4[i];
-        const float tc = tanhf(c_cur[i]);
+        const float tc = gate_tanh(c_cur[i]);
         const float d_o = dh * tc;
         const float dct = dc_reg[i] + dh * g.w * (1.f - tc * tc);
         const float d_i = dct * g.z, d_g = dct * g.x, d_f = dct * cp[i];
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
                                       d_g * (1.f - g.z * g.z), d_o * g.w * (1.f - g.w));
         dbacc[i].x += dp.x; dbacc[i].y += dp.y; dbacc[i].z += dp.z; dbacc[i].w += dp.w;
         *reinterpret_cast<float4*>(&dpre_s[rl][u * 4]) = dp;
-        *reinterpret_cast<float4*>(gates + (((size_t)t * B + row0 + rl) * H + j0 + u) * 4) = dp;
+        reinterpret_cast<float4*>(gates)[(uint32_t)t * BH + (uint32_t)(row0 + rl) * H + j0 + u] = dp;
       }
     }
     if (iter + 1 < T) prefetch(step - 1);
@@ -182,22 +182,43 @@ __global__ void __launch_bounds__(256, 1) rec_bwd_cluster_kernel(RecBwdArgs a, i
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       float2 acc[TKO / 2][RB];
+      if ((ch + 1) * RB <= nrows) {
+        // full chunk: no per-row predicates, accumulators start from the first product
 #pragma unroll
-      for (int kp = 0; kp < TKO / 2; ++kp)
+        for (int b = 0; b < RB; ++b) {
 #pragma unroll
-        for (int b = 0; b < RB; ++b) acc[kp][b] = make_float2(0.f, 0.f);
+          for (int mm = 0; mm < MM; ++mm) {
+            const float4 dv = *reinterpret_cast<const float4*>(&dpre_s[ch * RB + b][mm * 32 + ns * 4]);
+            const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
-      for (int b = 0; b < RB; ++b) {
-        if (ch * RB + b >= nrows) continue;  // uniform: rows this cluster does not own
+            for (int i = 0; i < 4; ++i) {
+              const float2 dup = make_float2(dvv[i], dvv[i]);
 #pragma unroll
-        for (int mm = 0; mm < MM; ++mm) {
-          const float4 dv = *reinterpret_cast<const float4*>(&dpre_s[ch * RB + b][mm * 32 + ns * 4]);
-          const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
+              for (int kp = 0; kp < TKO / 2; ++kp) {
+                if (mm == 0 && i == 0) acc[kp][b] = fmul2(dup, w2[mm][i][kp]);
+                else ffma2(acc[kp][b], dup, w2[mm][i][kp]);
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 dup = make_float2(dvv[i], dvv[i]);
+        for (int kp = 0; kp < TKO / 2; ++kp)
 #pragma unroll
-            for (int kp = 0; kp < TKO / 2; ++kp) ffma2(acc[kp][b], dup, w2[mm][i][kp]);
+          for (int b = 0; b < RB; ++b) acc[kp][b] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          if (ch * RB + b >= nrows) continue;  // uniform: rows this cluster does not own
+#pragma unroll
+          for (int mm = 0; mm < MM; ++mm) {
+            const float4 dv = *reinterpret_cast<const float4*>(&dpre_s[ch * RB + b][mm * 32 + ns * 4]);
+            const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 dup = make_float2(dvv[i], dvv[i]);
+#pragma unroll
+              for (int kp = 0; kp < TKO / 2; ++kp) ffma2(acc[kp][b], dup, w2[mm][i][kp]);
+            }
           }
         }
       }
@@ -293,6 +314,8 @@ static int launch_bwd(const RecBwdArgs& a, int slices, cudaStream_t stream) {
 void pick_partition(int H, int B, int D, int* slices_out, int* nch_out);
 
 int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream) {
+  MRG_REQUIRE((long long)(a.T + 1) * a.B * a.H * 4 * a.D < (1LL << 31),
+              "rec_backward_cluster: T*B*4H*D exceeds the 32-bit index range");
   int slices, nch;
   pick_partition(a.H, a.B, a.D, &slices, &nch);
   if (a.H == 256) {

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
   const int cid = blockIdx.x / CL;
   const int d = cid / slices;
   const int T = a.T, B = a.B;
+  const uint32_t BH = (uint32_t)B * H;
   // uneven row split: the first (B % slices) clusters take one row more
   const int sl = cid % slices, base_rows = B / slices, rem_rows = B % slices;
   const int row0 = sl * base_rows + min(sl, rem_rows);
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
       xg_n[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (step + 1 < T && valid[ch]) {
         const int tn = d == 0 ? t + 1 : t - 1;
-        xg_n[ch] = __ldcg(reinterpret_cast<const float4*>(
-            gates + (((size_t)tn * B + row0 + ch * RB + ob) * H + j) * 4));
+        xg_n[ch] = __ldcg(reinterpret_cast<const float4*>(gates) + (uint32_t)tn * BH +
+                          (uint32_t)(row0 + ch * RB + ob) * H + j);
       }
     }
     if (step > 0) {  // h_buf[cur] holds h_{t-1} of all 8 CTAs once its mbarrier phase completes
@@ -143,22 +144,41 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       float2 acc[NA][RB];
+      if ((ch + 1) * RB <= nrows) {
+        // full chunk (the common case): no per-row predicates, accumulators start from the first product
 #pragma unroll
-      for (int n = 0; n < NA; ++n)
+        for (int b = 0; b < RB; ++b) {
+          const float* hrow = &h_buf[cur][ch * RB + b][ks * 4];
 #pragma unroll
-        for (int b = 0; b < RB; ++b) acc[n][b] = make_float2(0.f, 0.f);
+          for (int m = 0; m < MK; ++m) {
+            const float4 h4 = *reinterpret_cast<const float4*>(hrow + m * 64);
+            const float2 hlo = make_float2(h4.x, h4.y), hhi = make_float2(h4.z, h4.w);
 #pragma unroll
-      for (int b = 0; b < RB; ++b) {
-        if (ch * RB + b >= nrows) continue;  // uniform: rows this cluster does not own
-        const float* hrow = &h_buf[cur][ch * RB + b][ks * 4];
+            for (int n = 0; n < NA; ++n) {
+              if (m == 0) acc[n][b] = fmul2(make_float2(w[n][m].x, w[n][m].y), hlo);
+              else ffma2(acc[n][b], make_float2(w[n][m].x, w[n][m].y), hlo);
+              ffma2(acc[n][b], make_float2(w[n][m].z, w[n][m].w), hhi);
+            }
+          }
+        }
+      } else {
 #pragma unroll
-        for (int m = 0; m < MK; ++m) {
-          const float4 h4 = *reinterpret_cast<const float4*>(hrow + m * 64);
-          const float2 hlo = make_float2(h4.x, h4.y), hhi = make_float2(h4.z, h4.w);
+        for (int n = 0; n < NA; ++n)
 #pragma unroll
-          for (int n = 0; n < NA; ++n) {
-            ffma2(acc[n][b], make_float2(w[n][m].x, w[n][m].y), hlo);
-            ffma2(acc[n][b], make_float2(w[n][m].z, w[n][m].w), hhi);
+          for (int b = 0; b < RB; ++b) acc[n][b] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+          if (ch * RB + b >= nrows) continue;  // uniform: rows this cluster does not own
+          const float* hrow = &h_buf[cur][ch * RB + b][ks * 4];
+#pragma unroll
+          for (int m = 0; m < MK; ++m) {
+            const float4 h4 = *reinterpret_cast<const float4*>(hrow + m * 64);
+            const float2 hlo = make_float2(h4.x, h4.y), hhi = make_float2(h4.z, h4.w);
+#pragma unroll
+            for (int n = 0; n < NA; ++n) {
+              ffma2(acc[n][b], make_float2(w[n][m].x, w[n][m].y), hlo);
+              ffma2(acc[n][b], make_float2(w[n][m].z, w[n][m].w), hhi);
+            }
           }
         }
       }
@@ -206,22 +226,23 @@ __global__ void __launch_bounds__(256, 1) rec_fwd_cluster_kernel(RecArgs a, int 
       if (valid[ch]) {
         const int rl = ch * RB + ob;
         const int row = row0 + rl;
-        const float gi = sigmoid_acc(v4[0] + xg[ch].x);
-        const float gf = sigmoid_acc(v4[1] + xg[ch].y);
-        const float gg = tanhf(v4[2] + xg[ch].z);
-        const float go = sigmoid_acc(v4[3] + xg[ch].w);
+        const float gi = gate_sigmoid(v4[0] + xg[ch].x);
+        const float gf = gate_sigmoid(v4[1] + xg[ch].y);
+        const float gg = gate_tanh(v4[2] + xg[ch].z);
+        const float go = gate_sigmoid(v4[3] + xg[ch].w);
         const float c = gf * c_reg[ch] + gi * gg;
-        const float h = go * tanhf(c);
+        const float h = go * gate_tanh(c);
         c_reg[ch] = c;
         if (send) {
           const uint32_t off = (uint32_t)(((nxt * R + rl) * H + j) * sizeof(float));
 #pragma unroll
           for (int r = 0; r < CL; ++r) st_async_f32(remote[r] + off, h, remote_bar[r] + nxt * 8);
         }
-        y_ext[((size_t)out_slot * B + row) * H + j] = h;
-        c_ext[((size_t)out_slot * B + row) * H + j] = c;
+        const uint32_t oidx = (uint32_t)out_slot * BH + (uint32_t)row * H + j;  // < 2^31 (host-checked)
+        y_ext[oidx] = h;
+        c_ext[oidx] = c;
         if (a.train)
-          *reinterpret_cast<float4*>(gates + (((size_t)t * B + row) * H + j) * 4) =
+          reinterpret_cast<float4*>(gates)[(uint32_t)t * BH + (uint32_t)row * H + j] =
               make_float4(gi, gf, gg, go);
       }
     }
@@ -303,6 +324,8 @@ void pick_partition(int H, int B, int D, int* slices_out, int* nch_out) {
 }
 
 int rec_forward_cluster(const RecArgs& a, cudaStream_t stream) {
+  MRG_REQUIRE((long long)(a.T + 1) * a.B * a.H * 4 < (1LL << 31),
+              "rec_forward_cluster: T*B*4H exceeds the 32-bit index range of one direction");
   int slices, nch;
   pick_partition(a.H, a.B, a.D, &slices, &nch);
   if (a.H == 256) {
