@@ -119,6 +119,11 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     g.M = T * B; g.N = 4 * H; g.K = I;
     if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
   }
+  if (T == 1 && (flags & MRG_F_ZERO_STATE)) {
+    bool zero = true;
+    for (int d = 0; d < D; ++d) zero = zero && !w[d].h0 && !w[d].c0;
+    if (zero) return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, (flags & MRG_F_TRAIN) ? 1 : 0, stream);
+  }
   RecArgs r = {};
   r.gates = gates;
   r.w_hh[0] = w[0].w_hh;
@@ -163,7 +168,10 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   r.db_part = db_part;
   r.T = T; r.B = B; r.H = H; r.D = D;
   int e;
-  if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) e = rec_backward_cluster(r, stream);
+  bool pointwise = (T == 1) && (flags & MRG_F_ZERO_STATE);
+  for (int d = 0; d < D; ++d) pointwise = pointwise && !g[d].dh0 && !g[d].dc0;
+  if (pointwise) e = cell_zero_state_backward(gates, c_ext, dy, dh_n, dc_n, db_part, B, H, D, stream);
+  else if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) e = rec_backward_cluster(r, stream);
   else e = rec_backward_generic(r, stream);
   if (e) return e;
 
@@ -181,7 +189,9 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       m.accumulate = acc; m.row_deinterleave_H = H;
       if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
     }
-    if (g[d].dw_hh) {
+    if (g[d].dw_hh && pointwise) {  // h_prev = 0: no contribution
+      if (!acc) MRG_CUDA_CHECK(cudaMemsetAsync(g[d].dw_hh, 0, (size_t)4 * H * H * sizeof(float), stream));
+    } else if (g[d].dw_hh) {
       const float* hprev = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : slot);
       GemmArgs m = {};
       m.a = dpre; m.a_sm = 1; m.a_sk = 4 * H;

@@ -190,6 +190,11 @@ struct RecBwdArgs {
 int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream);
 
+int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
+                            cudaStream_t stream);
+int cell_zero_state_backward(float* gates, const float* c_ext, const float* dy, const float* dh_n,
+                             const float* dc_n, float* db_part, int B, int H, int D, cudaStream_t stream);
+
 int colsum_deinterleave(const float* part, float* db, int B, int H, int accumulate,
                         cudaStream_t stream);
 int max_active_clusters(int H);

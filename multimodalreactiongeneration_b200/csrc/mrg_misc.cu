@@ -101,6 +101,73 @@ int colsum_deinterleave(const float* part, float* db, int B, int H, int accumula
 }
 
 // ---------------------------------------------------------------------------------------------
+// T == 1 from zero state: the LSTM layer degenerates to a pointwise cell on the projection
+// (c = i*g, h = o*tanh(c); W_hh and the forget gate are inert).  This is every predictor step of the
+// reference's rollout.  One thread per (direction, row, unit).
+// ---------------------------------------------------------------------------------------------
+__global__ void cell_zero_fwd_kernel(float* __restrict__ gates, float* __restrict__ y_ext,
+                                     float* __restrict__ c_ext, int B, int H, int D, int train) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_dir = (long long)B * H;
+  if (idx >= per_dir * D) return;
+  const int d = (int)(idx / per_dir);
+  const long long r = idx % per_dir;
+  float4* gp = reinterpret_cast<float4*>(gates) + idx;                // [D][1][B][H] float4
+  const float4 x = *gp;
+  const float gi = sigmoid_acc(x.x), gf = sigmoid_acc(x.y), gg = tanhf(x.z), go = sigmoid_acc(x.w);
+  const float c = gi * gg;
+  const float h = go * tanhf(c);
+  const long long out = (long long)d * 2 * per_dir + (d == 0 ? per_dir : 0) + r;  // dir0: slot 1, dir1: slot 0
+  y_ext[out] = h;
+  c_ext[out] = c;
+  if (train) *gp = make_float4(gi, gf, gg, go);
+}
+
+__global__ void cell_zero_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_ext,
+                                     const float* __restrict__ dy, const float* __restrict__ dh_n,
+                                     const float* __restrict__ dc_n, float* __restrict__ db_part, int B,
+                                     int H, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_dir = (long long)B * H;
+  if (idx >= per_dir * D) return;
+  const int d = (int)(idx / per_dir);
+  const long long r = idx % per_dir;
+  const int b = (int)(r / H), j = (int)(r % H);
+  float4* gp = reinterpret_cast<float4*>(gates) + idx;
+  const float4 g = *gp;
+  const float c = c_ext[(long long)d * 2 * per_dir + (d == 0 ? per_dir : 0) + r];
+  float dh = dh_n ? dh_n[idx] : 0.f;
+  if (dy) dh += dy[(long long)b * D * H + (long long)d * H + j];
+  const float tc = tanhf(c);
+  const float dct = (dc_n ? dc_n[idx] : 0.f) + dh * g.w * (1.f - tc * tc);
+  const float4 dp = make_float4(dct * g.z * g.x * (1.f - g.x), 0.f, dct * g.x * (1.f - g.z * g.z),
+                                dh * tc * g.w * (1.f - g.w));
+  *gp = dp;
+  reinterpret_cast<float4*>(db_part)[idx] = dp;                        // [D][B][H][4]
+}
+
+int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
+                            cudaStream_t stream) {
+  const long long n = (long long)B * H * D;
+  ProfScope prof(PROF_REC_FWD, stream);
+  count_launch();
+  cell_zero_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gates, y_ext, c_ext, B, H, D, train);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int cell_zero_state_backward(float* gates, const float* c_ext, const float* dy, const float* dh_n,
+                             const float* dc_n, float* db_part, int B, int H, int D, cudaStream_t stream) {
+  const long long n = (long long)B * H * D;
+  ProfScope prof(PROF_REC_BWD, stream);
+  count_launch();
+  cell_zero_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gates, c_ext, dy, dh_n, dc_n, db_part,
+                                                                        B, H, D);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) — must match oracle/philox.py bit for bit.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t philox4x32_10_first(uint32_t c0, uint32_t c1, uint32_t c2,

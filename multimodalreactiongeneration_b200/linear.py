@@ -1,0 +1,72 @@
+"""``B200Linear`` — ``nn.Linear`` whose three GEMMs (y = xWᵀ+b, dx = dy·W, dW = dyᵀ·x) run on the library's
+tcgen05 3xTF32 kernel (fp32-grade accuracy) instead of torch's fp32 SIMT sgemm.
+
+Used for the Linear layers that sit directly on the ``[B, T, 256]`` stream next to the LSTMs (SURVEY.md §8a
+rows a1/a2/a5: ``LSTMModule.mixer``, the bottleneck FFN of ``LSTMBlock``, ``embed_layer`` /
+``acoustic_projection`` / ``feature_projection`` / ``feed_forward``).  Same parameters, init and
+``state_dict`` keys as ``nn.Linear``; no CPU path."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _cabi
+from .lstm import _default_flags, _workspace
+
+
+def _gemm(a, a_sm, a_sk, b, b_sk, b_sn, bias, c, M, N, K, flags):
+    L = _cabi.lib()
+    dev = c.device
+    ws = _workspace(dev, L.mrg_gemm_workspace_bytes(M, N, K))
+    with torch.cuda.device(dev):
+        st = L.mrg_gemm_strided(a.data_ptr(), a_sm, a_sk, b.data_ptr(), b_sk, b_sn, _cabi.ptr(bias), c.data_ptr(),
+                                N, M, N, K, 0, 0, ws.data_ptr(), ws.numel(), flags,
+                                torch.cuda.current_stream(dev).cuda_stream)
+    _cabi.check(st, "mrg_gemm_strided")
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if not x.is_cuda:
+            raise RuntimeError("B200Linear has no CPU path: inputs must live on a B200 (sm_100a) device")
+        if x.dtype != torch.float32 or weight.dtype != torch.float32:
+            raise TypeError("B200Linear computes in fp32")
+        N, K = weight.shape
+        x2 = x.reshape(-1, K).contiguous()
+        M = x2.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        flags = _default_flags()
+        if M > 0:
+            _gemm(x2, K, 1, weight.contiguous(), 1, K, bias, y, M, N, K, flags)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.flags = flags
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        N, K = weight.shape
+        M = x2.shape[0]
+        dy2 = dy.reshape(-1, N).contiguous()
+        dx = dw = db = None
+        w = weight.contiguous()
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+            if M > 0:   # dx[M,K] = dy[M,N] · W[N,K]
+                _gemm(dy2, N, 1, w, K, 1, None, dx, M, K, N, ctx.flags)
+            dx = dx.view(*dy.shape[:-1], K)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros((N, K), dtype=torch.float32, device=dy.device) if M == 0 else \
+                torch.empty((N, K), dtype=torch.float32, device=dy.device)
+            if M > 0:   # dW[N,K] = dyᵀ[N,M] · x[M,K]
+                _gemm(dy2, 1, N, x2, K, 1, None, dw, N, K, M, ctx.flags)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(dim=0)
+        return dx, dw, db
+
+
+class B200Linear(nn.Linear):
+    def forward(self, input):  # noqa: A002 - nn.Linear's argument name
+        return _LinearFn.apply(input, self.weight, self.bias)

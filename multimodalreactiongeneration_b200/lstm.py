@@ -77,6 +77,8 @@ class _LSTMLayerFn(torch.autograd.Function):
             keep += [h0d, c0d]
             dw[d] = _cabi.DirWeights(_cabi.ptr(w_ih), _cabi.ptr(w_hh), _cabi.ptr(b_ih), _cabi.ptr(b_hh),
                                      _cabi.ptr(h0d), _cabi.ptr(c0d))
+        if h0 is None and c0 is None:
+            flags |= _cabi.F_ZERO_STATE
         fl = flags | (_cabi.F_TRAIN if need_grad else 0)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):

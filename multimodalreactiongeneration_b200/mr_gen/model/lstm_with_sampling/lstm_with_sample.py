@@ -9,12 +9,23 @@ with ``torch.rand`` when no mask is supplied), Q5 one-frame lag of teacher forci
 Q6 gradients flow through fed-back predictions, Q7 loss averaged over padded positions too.
 
 Extensions (BASELINE.json north_star): ``sampling_mask`` may be supplied ([T] or [T, B] bool) — e.g.
-from the counter-based Philox generator (``philox_sampling_mask``), bit-exact for a given seed."""
+from the counter-based Philox generator (``philox_sampling_mask``), bit-exact for a given seed.
+
+Device-resident rollout (``rollout="wavefront"``, the default on CUDA).  Because of Q2 the predictor
+restarts from zero state at every step, so step t depends on step t-1 ONLY through the fed-back 6..18-d
+pose, and only where the mask says "feed the prediction back".  The rollout is therefore re-scheduled
+without changing any arithmetic: the sampler LSTM runs ONCE over lead+sequence (identical recurrence to the
+reference's carried-state calls), the audio/partner part of ``feature_projection`` is time-parallel, and the
+positions are processed in waves of equal feedback depth (depth[t] = depth[t-1]+1 if mask[t-1] else 0):
+wave d needs only wave d-1.  There is no per-step host loop — the number of launches is proportional to
+the longest run of fed-back steps, not to T — and autograd carries Q6 through the gathers."""
 from collections import OrderedDict
 from typing import List, Optional, Tuple
 
 import torch
 from torch import nn
+
+from ....linear import B200Linear
 
 from ....import _cabi
 from ...utils.lightning_shim import LightningModule
@@ -56,21 +67,21 @@ class LSTMwithSample(LightningModule):
         pose = (model.use_centroid + model.use_angle) * 3 * (model.delta_order + 1)
         acoustic_in = (model.nmels + 1) * (model.delta_order + 1)
 
-        self.acoustic_projection = nn.Linear(acoustic_in, model.sampler_hidden_size)
+        self.acoustic_projection = B200Linear(acoustic_in, model.sampler_hidden_size)
         self.sampling_lstm = LSTMSampler(model.sampler_hidden_size, model.sampler_num_layers,
                                          model.sampler_dropout_rate, self.ratio, bidirectional=False)
         self.use_device = "cuda" if torch.cuda.is_available() else "cpu"
-        self.feature_projection = nn.Linear(2 * pose + model.sampler_hidden_size, model.hidden_size)
+        self.feature_projection = B200Linear(2 * pose + model.sampler_hidden_size, model.hidden_size)
         self.layerd_lstm = LSTMLayerd(
             input_size=model.hidden_size, lstm_hidden_size=model.hidden_size,
             affine_hidden_size=model.hidden_size, bottleneck_size=model.bottleneck_size,
             num_layers=model.num_layers, num_layers_per_block=model.num_lstm, output_size=model.hidden_size,
             dropout=model.dropout_rate, bidirectional=False, use_layer_norm=model.use_layer_norm,
             use_mixing=model.use_mixing, use_residual=model.use_residual, use_feed_forward=False)
-        head = [("input", nn.Linear(model.hidden_size, model.bottleneck_size))]
+        head = [("input", B200Linear(model.hidden_size, model.bottleneck_size))]
         if model.use_relu:
             head.append(("relu", nn.ReLU()))
-        head.append(("mapping", nn.Linear(model.bottleneck_size, pose)))
+        head.append(("mapping", B200Linear(model.bottleneck_size, pose)))
         self.feed_forward = nn.Sequential(OrderedDict(head))
 
         ranges = gen_target_dict(metrics)
@@ -86,6 +97,8 @@ class LSTMwithSample(LightningModule):
         self.sampling_seed: Optional[int] = model.get("sampling_seed", None)
         self.sampling_offset = 0
         self.sampling_per_sample = model.get("sampling_per_sample", True)
+        # "wavefront": device-resident re-scheduled rollout; "stepwise": the reference's Python time loop
+        self.rollout = model.get("rollout", "wavefront")
 
     # ------------------------------------------------------------------------------------------
     def forward(self, acoustic_partner: InputTypes, motion_partner: InputTypes, motion_self: InputTypes,
@@ -171,12 +184,74 @@ class LSTMwithSample(LightningModule):
     # ------------------------------------------------------------------------------------------
     def prediction(self, batch: List[InputTypes], use_scheduled_sampling: bool = False,
                    full_generation: bool = False, sampling_mask: Optional[torch.Tensor] = None):
+        if self.rollout == "wavefront":
+            return self._prediction_wavefront(batch, use_scheduled_sampling, full_generation, sampling_mask)
         formed, dummy, length = self.batch_forming(batch)
         target = batch[-1][0].to(self.device)
         state = self.warmup_model(dummy, batch)
         pred = self.head_motion_generation(formed, dummy, length, state, use_scheduled_sampling,
                                            full_generation, sampling_mask)
         return pred, target
+
+    def _resolve_mask(self, length, batch_size, use_scheduled_sampling, full_generation, sampling_mask):
+        if sampling_mask is None:
+            if use_scheduled_sampling:
+                sampling_mask = self.draw_sampling_mask(length, batch_size)
+            else:
+                sampling_mask = torch.full((length,), bool(full_generation), dtype=torch.bool)
+        return sampling_mask
+
+    def _prediction_wavefront(self, batch, use_scheduled_sampling, full_generation, sampling_mask):
+        dev = self.device
+        (a, _), (mp, _), (ms, _), (la, _), (lp, _), (ls, _) = batch[:6]
+        a, mp, ms, la = a.to(dev), mp.to(dev), ms.to(dev), la.to(dev)
+        target = batch[-1][0].to(dev)
+        B, T, P = mp.shape
+        mask = self._resolve_mask(T, B, use_scheduled_sampling, full_generation, sampling_mask)
+        if T == 0:
+            return ms.new_zeros((B, 0, P)), target
+        mask = mask.to(dev)
+        if mask.dim() == 1:
+            mask = mask.view(T, 1).expand(T, B)
+        # --- time-parallel part -----------------------------------------------------------------
+        lead_frames = la.shape[1] // self.ratio
+        audio = self.acoustic_projection(torch.cat([la, a], dim=1))
+        sampled, _ = self.sampling_lstm(audio, None)          # one recurrence over lead + sequence
+        sampled = sampled[:, lead_frames:]                     # [B, T, Hs]
+        Hs = sampled.shape[-1]
+        W, bias = self.feature_projection.weight, self.feature_projection.bias
+        base = torch.nn.functional.linear(torch.cat([sampled, mp], dim=-1), W[:, :Hs + P], bias)  # [B,T,Hd]
+        W_prev = W[:, Hs + P:]                                 # [Hd, P]
+        base = base.reshape(B * T, -1)
+        # --- feedback depth of every (b, t) -----------------------------------------------------
+        t_idx = torch.arange(T, device=dev).view(T, 1)
+        last_false = torch.where(mask, torch.full_like(t_idx, -1), t_idx).cummax(dim=0).values  # [T,B]
+        depth = torch.zeros((T, B), dtype=torch.long, device=dev)
+        depth[1:] = (t_idx - last_false)[:-1]
+        depth = depth.t().reshape(-1)                           # position p = b*T + t
+        order = torch.argsort(depth, stable=True)
+        counts = torch.bincount(depth).tolist()                 # the one host read of the rollout
+        starts = [0]
+        for c in counts:
+            starts.append(starts[-1] + c)
+        slot = torch.empty_like(order)
+        slot[order] = torch.arange(B * T, device=dev) - torch.tensor(starts[:-1], device=dev)[depth[order]]
+        # ground-truth previous frame with the reference's one-frame lag (Q5): ms[0], ms[0], ms[1], ...
+        gt_prev = torch.cat([ms[:, :1], ms[:, :-1]], dim=1).reshape(B * T, P)
+        outs = []
+        for d, n in enumerate(counts):
+            if n == 0:
+                outs.append(base.new_zeros((0, P)))
+                continue
+            idx = order[starts[d]:starts[d + 1]]
+            prev = gt_prev.index_select(0, idx) if d == 0 else outs[d - 1].index_select(0, slot[idx - 1])
+            x = base.index_select(0, idx) + torch.nn.functional.linear(prev, W_prev)
+            h, _ = self.layerd_lstm(x.unsqueeze(1), None)       # stateless predictor blocks (Q2), T = 1
+            outs.append(self.feed_forward(h).squeeze(1))
+        inverse = torch.empty_like(order)
+        inverse[order] = torch.arange(B * T, device=dev)
+        pred = torch.cat(outs, dim=0).index_select(0, inverse).view(B, T, P)
+        return pred.contiguous(), target
 
     def batch_forming(self, batch):
         formed, length = self.form_generation_init(batch)
@@ -203,11 +278,8 @@ class LSTMwithSample(LightningModule):
                                sampling_mask: Optional[torch.Tensor] = None):
         motion_s = formed_batch[2][0]
         batch_size = motion_s.shape[1]
-        if sampling_mask is None:
-            if use_scheduled_sampling:
-                sampling_mask = self.draw_sampling_mask(length, batch_size)
-            else:
-                sampling_mask = torch.full((length,), bool(full_generation), dtype=torch.bool)
+        sampling_mask = self._resolve_mask(length, batch_size, use_scheduled_sampling, full_generation,
+                                           sampling_mask)
         per_sample = sampling_mask.dim() == 2
         if per_sample:
             sampling_mask = sampling_mask.to(motion_s.device)

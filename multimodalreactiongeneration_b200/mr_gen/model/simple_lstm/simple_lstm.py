@@ -10,6 +10,8 @@ from typing import Dict
 import torch
 from torch import nn
 
+from ....linear import B200Linear
+
 from ...utils.lightning_shim import LightningModule
 from ...utils.metrics import MultiTargetMetrics, gen_target_dict
 from ..utils.lstm_block import LSTMLayerd
@@ -19,7 +21,7 @@ from ..utils.multi_modal_att import MultimodalAttention
 class AcousticEncoder(nn.Module):
     def __init__(self, cfg) -> None:
         super().__init__()
-        self.embed_layer = nn.Linear(cfg.acostic_feat_size, cfg.acostic_affine_size)
+        self.embed_layer = B200Linear(cfg.acostic_feat_size, cfg.acostic_affine_size)
         self.acostic_lstm = LSTMLayerd(
             input_size=cfg.acostic_affine_size, lstm_hidden_size=cfg.acostic_lstm_size,
             affine_hidden_size=cfg.acostic_affine_size, num_layers=cfg.acostic_num_layers,
@@ -34,7 +36,7 @@ class AcousticEncoder(nn.Module):
 class MotionEncoder(nn.Module):
     def __init__(self, cfg) -> None:
         super().__init__()
-        self.embed_layer = nn.Linear(cfg.motion_feat_size, cfg.motion_affine_size)
+        self.embed_layer = B200Linear(cfg.motion_feat_size, cfg.motion_affine_size)
         self.motion_lstm = LSTMLayerd(
             input_size=cfg.motion_affine_size, lstm_hidden_size=cfg.motion_lstm_size,
             affine_hidden_size=cfg.motion_affine_size, num_layers=cfg.motion_num_layers,
@@ -57,10 +59,10 @@ class MotionDecoder(nn.Module):
             bidirectional=cfg.decoder_bidirectional, use_layer_norm=cfg.decoder_use_layer_norm,
             use_relu=cfg.decoder_use_relu, use_mixing=cfg.decoder_use_mixing,
             use_residual=cfg.decoder_use_residual)
-        head = [("input", nn.Linear(cfg.decoder_output_size, cfg.decoder_mapping_size))]
+        head = [("input", B200Linear(cfg.decoder_output_size, cfg.decoder_mapping_size))]
         if cfg.decoder_use_relu:
             head.append(("relu", nn.ReLU()))
-        head.append(("output", nn.Linear(cfg.decoder_mapping_size, cfg.output_size)))
+        head.append(("output", B200Linear(cfg.decoder_mapping_size, cfg.output_size)))
         self.mapping = nn.Sequential(OrderedDict(head))
 
     def seq_reshape(self, x: torch.Tensor) -> torch.Tensor:

@@ -11,6 +11,7 @@ import torch
 from torch import nn
 
 from ....lstm import B200LSTM
+from ....linear import B200Linear
 from .residual_connection import ResidualConnection
 
 State = Tuple[torch.Tensor, torch.Tensor]
@@ -25,7 +26,7 @@ class LSTMModule(nn.Module):
             raise ValueError("lstm_out_size must be equal to output_size when use_mixing is False.")
         self.lstm_module = B200LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
                                     dropout=dropout, batch_first=True, bidirectional=bidirectional)
-        self.mixer = nn.Linear(width, output_size) if use_mixing else None
+        self.mixer = B200Linear(width, output_size) if use_mixing else None
 
     def forward(self, input_tensor, hx=None) -> Tuple[torch.Tensor, State]:
         hs, hx = self.lstm_module(input_tensor, hx)
@@ -46,10 +47,10 @@ class LSTMBlock(nn.Module):
                           use_mixing=use_mixing)
         self.lstm_module = ResidualConnection(core, use_layer_norm, lstm_out_size, dropout) if use_residual else core
         if use_feed_forward:
-            parts = [("input", nn.Linear(lstm_out_size, bottleneck_size))]
+            parts = [("input", B200Linear(lstm_out_size, bottleneck_size))]
             if use_relu:
                 parts.append(("relu", nn.ReLU()))
-            parts.append(("mapping", nn.Linear(bottleneck_size, output_size)))
+            parts.append(("mapping", B200Linear(bottleneck_size, output_size)))
             ffn = nn.Sequential(OrderedDict(parts))
             self.feed_forward_module = (ResidualConnection(ffn, use_layer_norm, output_size, dropout)
                                         if use_residual else ffn)

@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from ....lstm import B200LSTM
+from ....linear import B200Linear
 from .residual_connection import ResidualConnection
 
 LSTMStateType = Tuple[torch.Tensor, torch.Tensor]
@@ -47,11 +48,11 @@ class FeedForward(nn.Module):
         if residual and hidden_size != output_size:
             raise ValueError("hidden_size must be equal to output_size when residual is True.")
         if nonlinearity is None or nonlinearity == "none":
-            layers = [("feedforward", nn.Linear(hidden_size, output_size, **kw))]
+            layers = [("feedforward", B200Linear(hidden_size, output_size, **kw))]
         else:
-            layers = [("input", nn.Linear(hidden_size, bottleneck_size, **kw)),
+            layers = [("input", B200Linear(hidden_size, bottleneck_size, **kw)),
                       ("activation", set_nonlinearity(nonlinearity)()),
-                      ("output", nn.Linear(bottleneck_size, output_size, **kw))]
+                      ("output", B200Linear(bottleneck_size, output_size, **kw))]
         ff = nn.Sequential(OrderedDict(layers))
         self.feed_forward = ResidualConnection(ff, residual_layer_norm, hidden_size) if residual else ff
 
@@ -125,8 +126,8 @@ class LSTMMixerLayerd(nn.Module):
             raise ValueError("input_projection_size must be specified when input_projection is True.")
         if output_projection and output_projection_size is None:
             raise ValueError("output_projection_size must be specified when output_projection is True.")
-        self.input_projection = nn.Linear(input_projection_size, hidden_size, **kw) if input_projection else None
-        self.output_projection = (nn.Linear(output_projection_size, hidden_size, **kw)
+        self.input_projection = B200Linear(input_projection_size, hidden_size, **kw) if input_projection else None
+        self.output_projection = (B200Linear(output_projection_size, hidden_size, **kw)
                                   if output_projection else None)
         self.mixer = nn.ModuleList(
             LSTMMixerBlock(hidden_size=hidden_size, num_layers=num_internal_layer, dropout=dropout,

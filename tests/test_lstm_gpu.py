@@ -183,3 +183,27 @@ def test_strided_gemm_all_majors(a_mn, b_mn, M, N, K, deint):
         _cabi.check(st, "mrg_gemm_strided")
         torch.cuda.synchronize()
         assert rel_err(c.cpu(), ref) <= (5e-6 if flags == 0 else 2e-6), (flags, a_mn, b_mn)
+
+
+@pytest.mark.parametrize("H,bi", [(256, False), (32, True)])
+def test_single_step_zero_state_pointwise_path(H, bi):
+    """T == 1 with hx=None takes the pointwise cell kernels (no recurrence); must equal torch.nn.LSTM."""
+    ref, mine = _build(H, H, 1, bi)
+    D = 2 if bi else 1
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(37, 1, H, generator=g, dtype=torch.double)
+    wy = torch.randn(37, 1, D * H, generator=g, dtype=torch.double)
+    wc = torch.randn(D, 37, H, generator=g, dtype=torch.double)
+    xr = x.clone().requires_grad_(True)
+    yr, (hr, cr) = ref(xr)
+    ((yr * wy).sum() + (cr * wc).sum() + hr.sum()).backward()
+    xm = x.float().cuda().requires_grad_(True)
+    ym, (hm, cm) = mine(xm)
+    ((ym * wy.float().cuda()).sum() + (cm * wc.float().cuda()).sum() + hm.sum()).backward()
+    assert rel_err(ym.cpu(), yr) <= STATE_TOL and rel_err(cm.cpu(), cr) <= STATE_TOL
+    assert rel_l2(xm.grad.cpu(), xr.grad) <= GRAD_TOL
+    for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        if "weight_hh" in name:
+            assert float(pm.grad.abs().max()) == 0.0 and float(pr.grad.abs().max()) == 0.0
+        else:
+            assert rel_l2(pm.grad.cpu(), pr.grad) <= GRAD_TOL, name

@@ -178,3 +178,39 @@ def test_lstm_mixer_layerd_matches_reference():
     assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
     assert rel_l2(x.grad.cpu(), grads["x"]) <= GRAD_TOL
     _check_grads(m, grads)
+
+
+def test_wavefront_rollout_equals_stepwise_loop_with_philox_masks():
+    """The re-scheduled device-resident rollout vs the reference's step-by-step loop, at the real hidden
+    sizes (cluster kernels), with per-sample Philox masks; forward, loss and every gradient."""
+    from multimodalreactiongeneration_b200.mr_gen.configs import lstm_with_sampling_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstm_with_sampling.lstm_with_sample import (
+        LSTMwithSample, philox_sampling_mask)
+    from oracle import philox
+    B, T, lead, ratio = 5, 12, 3, 2
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    batch = [(r(B, T * ratio, 80), None), (r(B, T, 6), None), (r(B, T, 6), None), (r(B, lead * ratio, 80), None),
+             (r(B, lead, 6), None), (r(B, lead, 6), None), (r(B, T, 6), None)]
+    results = {}
+    for mode in ("stepwise", "wavefront"):
+        torch.manual_seed(0)
+        m = LSTMwithSample(*lstm_with_sampling_cfg(max_epochs=10, ratio=ratio, seed=4321)).cuda()
+        m.rollout = mode
+        m.current_epoch = 5
+        mask = philox_sampling_mask(4321, 0, 0.5, T, B, "cuda")
+        assert (mask.cpu().numpy() == philox.sampling_mask(4321, 0, 0.5, T, B)).all()  # bit-exact masks
+        assert 0 < int(mask.sum()) < T * B
+        loss = m.training_step(batch)["loss"]          # draws the same Philox mask internally (seed, offset 0)
+        assert m.sampling_offset == T
+        loss.backward()
+        with torch.no_grad():
+            pred, _ = m.prediction(batch, use_scheduled_sampling=True, sampling_mask=mask)
+            free, _ = m.prediction(batch, full_generation=True)
+        results[mode] = (loss.detach(), pred, free, {k: p.grad.clone() for k, p in m.named_parameters()})
+    (l0, p0, f0, g0), (l1, p1, f1, g1) = results["stepwise"], results["wavefront"]
+    assert abs(float(l0) - float(l1)) <= 1e-5 * abs(float(l0))
+    assert rel_err(p1, p0) <= OUT_TOL
+    assert rel_err(f1, f0) <= 5e-5
+    for k in g0:
+        assert rel_l2(g1[k], g0[k]) <= GRAD_TOL, k
