@@ -111,6 +111,23 @@ int mrg_gemm_strided(const float* a, long long a_sm, long long a_sk, const float
                      void* stream);
 size_t mrg_gemm_workspace_bytes(int M, int N, int K);
 
+/* Fused residual + LayerNorm — ResidualConnection.forward, mr_gen/model/utils/residual_connection.py:29-32:
+ * out = LN(y + x) * gamma + beta over the last dimension (H in {128, 256, 512}).  Rows are indexed (i0, i1),
+ * i0 < n0, i1 < n1, with element strides (s0, s1) per tensor, so a time-major LSTM output and a batch-first
+ * block input are read in place.  x may be NULL (plain LayerNorm).  mean / rstd: [n0*n1], kept for the
+ * backward, which recomputes y + x and returns dsum = d(y) = d(x) plus d(gamma), d(beta). */
+size_t mrg_layernorm_workspace_bytes(int H);
+int mrg_residual_layernorm_forward(const float* y, long long y_s0, long long y_s1, const float* x,
+                                   long long x_s0, long long x_s1, const float* gamma, const float* beta,
+                                   float* out, long long o_s0, long long o_s1, float* mean, float* rstd,
+                                   int n0, int n1, int H, float eps, void* stream);
+int mrg_residual_layernorm_backward(const float* dout, long long d_s0, long long d_s1, const float* y,
+                                    long long y_s0, long long y_s1, const float* x, long long x_s0,
+                                    long long x_s1, const float* gamma, const float* mean, const float* rstd,
+                                    float* dsum, long long g_s0, long long g_s1, float* dgamma, float* dbeta,
+                                    void* workspace, size_t workspace_bytes, int n0, int n1, int H,
+                                    void* stream);
+
 /* Scheduled-sampling mask: out[t*B+b] = philox4x32_10(ctr=(lo(offset+t), hi(offset+t), shared?0:b, 0),
  * key=(lo(seed), hi(seed)))[0] >> 8 as a 24-bit uniform < prob.  out is a DEVICE uint8 buffer. */
 int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared, uint8_t* out,

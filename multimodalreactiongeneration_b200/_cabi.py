@@ -14,7 +14,8 @@ EXPORTS = (
     "mrg_version", "mrg_last_error_string", "mrg_device_info", "mrg_lstm_workspace_bytes",
     "mrg_lstm_layer_forward", "mrg_lstm_layer_backward", "mrg_gemm_nt", "mrg_philox_mask",
     "mrg_launch_count", "mrg_profile_enable", "mrg_profile_read", "mrg_gemm_strided",
-    "mrg_gemm_workspace_bytes",
+    "mrg_gemm_workspace_bytes", "mrg_layernorm_workspace_bytes", "mrg_residual_layernorm_forward",
+    "mrg_residual_layernorm_backward",
 )
 
 
@@ -71,6 +72,15 @@ def lib() -> ctypes.CDLL:
     L.mrg_gemm_strided.restype = c_int
     L.mrg_gemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.mrg_gemm_workspace_bytes.restype = c_size_t
+    L.mrg_layernorm_workspace_bytes.argtypes = [c_int]
+    L.mrg_layernorm_workspace_bytes.restype = c_size_t
+    L.mrg_residual_layernorm_forward.argtypes = [c_void_p, LL, LL, c_void_p, LL, LL, c_void_p, c_void_p, c_void_p,
+                                                 LL, LL, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
+    L.mrg_residual_layernorm_forward.restype = c_int
+    L.mrg_residual_layernorm_backward.argtypes = [c_void_p, LL, LL, c_void_p, LL, LL, c_void_p, LL, LL, c_void_p,
+                                                  c_void_p, c_void_p, c_void_p, LL, LL, c_void_p, c_void_p, c_void_p,
+                                                  c_size_t, c_int, c_int, c_int, c_void_p]
+    L.mrg_residual_layernorm_backward.restype = c_int
     L.mrg_launch_count.restype = ctypes.c_ulonglong
     L.mrg_profile_enable.argtypes = [c_int]
     L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]

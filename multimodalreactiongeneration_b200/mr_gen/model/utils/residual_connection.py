@@ -1,6 +1,8 @@
 """Mirror of mr_gen/model/utils/residual_connection.py:5-37 (``y = Dropout(LN(module(x) + x))``)."""
 from torch import nn
 
+from .... import layernorm as _fused_ln
+
 
 class ResidualConnection(nn.Module):
     """Wraps ``module``; extra tuple outputs (LSTM states) pass through untouched.
@@ -22,8 +24,13 @@ class ResidualConnection(nn.Module):
         extras = None
         if isinstance(out, (tuple, list)):
             out, extras = out[0], tuple(out[1:])
-        out = out + x
-        if self.layer_norm is not None:
-            out = self.layer_norm(out)
+        ln = self.layer_norm
+        if ln is not None and ln.elementwise_affine and ln.bias is not None and _fused_ln.supported(out, x):
+            # one pass over the [B, T, H] stream: add + LayerNorm fused, strides consumed in place
+            out = _fused_ln.residual_layer_norm(out, x, ln.weight, ln.bias, ln.eps)
+        else:
+            out = out + x
+            if ln is not None:
+                out = ln(out)
         out = self.dropout(out)
         return out if extras is None else (out, *extras)

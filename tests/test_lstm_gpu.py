@@ -207,3 +207,30 @@ def test_single_step_zero_state_pointwise_path(H, bi):
             assert float(pm.grad.abs().max()) == 0.0 and float(pr.grad.abs().max()) == 0.0
         else:
             assert rel_l2(pm.grad.cpu(), pr.grad) <= GRAD_TOL, name
+
+
+@pytest.mark.parametrize("H", [128, 256, 512])
+@pytest.mark.parametrize("y_time_major", [False, True])
+def test_fused_residual_layernorm(H, y_time_major):
+    from multimodalreactiongeneration_b200.layernorm import residual_layer_norm
+    g = torch.Generator().manual_seed(8)
+    B, T = 7, 13
+    y0 = torch.randn(B, T, H, generator=g, dtype=torch.double)
+    x0 = torch.randn(B, T, H, generator=g, dtype=torch.double)
+    w0 = torch.randn(B, T, H, generator=g, dtype=torch.double)
+    gamma0 = torch.randn(H, generator=g, dtype=torch.double)
+    beta0 = torch.randn(H, generator=g, dtype=torch.double)
+    leaves = [t.clone().requires_grad_(True) for t in (y0, x0, gamma0, beta0)]
+    ref = torch.nn.functional.layer_norm(leaves[0] + leaves[1], (H,), leaves[2], leaves[3])
+    (ref * w0).sum().backward()
+    if y_time_major:  # LSTM output: time-major memory viewed batch-first
+        y = y0.float().transpose(0, 1).contiguous().cuda().transpose(0, 1).requires_grad_(True)
+    else:
+        y = y0.float().cuda().requires_grad_(True)
+    x = x0.float().cuda().requires_grad_(True)
+    gamma, beta = gamma0.float().cuda().requires_grad_(True), beta0.float().cuda().requires_grad_(True)
+    out = residual_layer_norm(y, x, gamma, beta, 1e-5)
+    (out * w0.float().cuda()).sum().backward()
+    assert rel_err(out.cpu(), ref) <= 2e-6
+    for got, want in zip((y, x, gamma, beta), leaves):
+        assert rel_l2(got.grad.cpu(), want.grad) <= 1e-5
