@@ -62,7 +62,8 @@ extern "C" int mrg_device_info(int* sm_count, int* max_clusters_h256, int* max_c
 extern "C" size_t mrg_lstm_workspace_bytes(int T, int B, int I, int H, int D) {
   if (T < 0 || B <= 0 || I <= 0 || H <= 0 || D < 1 || D > 2) return 0;
   const size_t head = align_up((size_t)D * 4 * H * sizeof(float), 256) +
-                      align_up((size_t)D * B * 4 * H * sizeof(float), 256);
+                      align_up((size_t)D * B * 4 * H * sizeof(float), 256) +
+                      (T == 1 ? align_up((size_t)D * 4 * H * H * sizeof(float), 256) : 0);
   size_t g = gemm_ws(T * B, 4 * H, I);
   size_t v = gemm_ws(T * B, I, 4 * H);
   if (v > g) g = v;
@@ -97,9 +98,18 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   float* bias_pack = (float*)ws;
   ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
   ws += align_up((size_t)D * B * 4 * H * sizeof(float), 256);
+  // T == 1: no recurrence to run — the step is projection GEMM(s) + a pointwise cell
+  bool single_zero = (T == 1) && (flags & MRG_F_ZERO_STATE);
+  for (int d = 0; d < D; ++d) single_zero = single_zero && !w[d].h0 && !w[d].c0;
+  const bool single_state = (T == 1) && !single_zero;
+  float* whh_pack = nullptr;
+  if (T == 1) {
+    if (single_state) whh_pack = (float*)ws;
+    ws += align_up((size_t)D * 4 * H * H * sizeof(float), 256);
+  }
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
 
-  if (int e = pack_weights(w, w_pack, bias_pack, I, H, D, stream)) return e;
+  if (int e = pack_weights(w, w_pack, bias_pack, whh_pack, I, H, D, stream)) return e;
   const size_t slot = (size_t)B * H;
   for (int d = 0; d < D; ++d) {
     float* ys = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : (size_t)T * slot);
@@ -119,10 +129,19 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     g.M = T * B; g.N = 4 * H; g.K = I;
     if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
   }
-  if (T == 1 && (flags & MRG_F_ZERO_STATE)) {
-    bool zero = true;
-    for (int d = 0; d < D; ++d) zero = zero && !w[d].h0 && !w[d].c0;
-    if (zero) return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, (flags & MRG_F_TRAIN) ? 1 : 0, stream);
+  if (single_zero)
+    return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, (flags & MRG_F_TRAIN) ? 1 : 0, 0, stream);
+  if (single_state) {
+    // gates += h0 * W_hh^T (second projection), then the pointwise cell with the carried c0
+    for (int d = 0; d < D; ++d) {
+      GemmArgs g = {};
+      g.a = y_ext + (size_t)d * 2 * slot + (d == 0 ? 0 : slot); g.a_sm = H; g.a_sk = 1;
+      g.b = whh_pack + (size_t)d * 4 * H * H; g.b_sk = 1; g.b_sn = H;
+      g.c = gates + (size_t)d * B * 4 * H; g.ldc = 4 * H;
+      g.M = B; g.N = 4 * H; g.K = H; g.accumulate = 1;
+      if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
+    }
+    return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, (flags & MRG_F_TRAIN) ? 1 : 0, 1, stream);
   }
   RecArgs r = {};
   r.gates = gates;
@@ -152,6 +171,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
   float* db_part = (float*)ws;
   ws += align_up((size_t)D * B * 4 * H * sizeof(float), 256);
+  if (T == 1) ws += align_up((size_t)D * 4 * H * H * sizeof(float), 256);
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   const int acc = (flags & MRG_F_ACCUMULATE) ? 1 : 0;
 

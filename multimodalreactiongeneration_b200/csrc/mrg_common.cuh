@@ -159,8 +159,8 @@ struct GemmArgs {
 int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_simt_workspace_bytes(int M, int N, int K);
 
-int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, int I, int H, int D,
-                 cudaStream_t stream);
+int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, float* whh_pack, int I, int H,
+                 int D, cudaStream_t stream);
 
 struct RecArgs {
   float* gates;        // [D][T][B][H][4]
@@ -191,7 +191,7 @@ int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream);
 
 int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
-                            cudaStream_t stream);
+                            int has_state, cudaStream_t stream);
 int cell_zero_state_backward(float* gates, const float* c_ext, const float* dy, const float* dh_n,
                              const float* dc_n, float* db_part, int B, int H, int D, cudaStream_t stream);
 

@@ -6,7 +6,8 @@
 //
 // One 128x128 output tile per CTA (x split-K slices), BLOCK_K = 32 fp32 = one 128-byte swizzle row.
 // Warp roles:  0 TMA producer | 1 MMA issuer (one elected thread) | 2 TMEM allocator | 3 idle |
-//              4-7 converter (raw fp32 tile -> hi / lo TF32 tiles in shared memory), then epilogue.
+//              4-11 converter (raw fp32 tile -> hi / lo TF32 tiles in shared memory); all 8 warps run the
+//              epilogue (TMEM -> padded smem tile -> coalesced 512-byte row stores).
 // Pipelines (mbarriers): full[s] TMA->converter, cvt[s] converter->MMA, empty[s] MMA->TMA
 // (tcgen05.commit), acc_full MMA->epilogue.
 //
@@ -39,11 +40,11 @@ struct TcParams {
   float* partial;       // split-K partial sums [gridDim.z][M][N] or nullptr
 };
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the low 13
+// bits) with two full-rate integer ops instead of cvt.rna.tf32.f32 (a quarter-rate conversion-pipe op).
+// lo = x - hi is exact in fp32 and is handed to the tensor core as is: it ignores the low 13 mantissa
+// bits of a tf32 operand, an error of 2^-10 relative to lo, i.e. 2^-21 relative to x.
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -87,7 +88,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int CVT_WARPS = 8;
+constexpr int TC_THREADS = 128 + CVT_WARPS * 32;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -109,7 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(cvt_bar(s), 4);
+      mbar_init(cvt_bar(s), CVT_WARPS);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -148,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
+    __syncwarp();  // lanes 1-31 park here (no spinning) until the producer lane is done
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -179,9 +184,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       umma_commit(acc_bar);         // accumulator complete
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== converter, then epilogue =====================
-    const int ct = threadIdx.x - 128;  // 0..127
+    const int ct = threadIdx.x - 128;  // 0 .. CVT_WARPS*32-1
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES, ph = (i / STAGES) & 1;
       mbar_wait(full_bar(s), ph);
@@ -191,15 +197,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         float4* hi = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES);
         float4* lo = reinterpret_cast<float4*>(st + op * 2 * TILE_BYTES + TILE_BYTES);
 #pragma unroll
-        for (int j = 0; j < TILE_BYTES / 16 / 128; ++j) {
-          const int e = ct + j * 128;
+        for (int j = 0; j < TILE_BYTES / 16 / (CVT_WARPS * 32); ++j) {
+          const int e = ct + j * (CVT_WARPS * 32);
           const float4 v = hi[e];
           uint4 h, l;
           h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - __uint_as_float(h.x));
-          l.y = tf32_rna(v.y - __uint_as_float(h.y));
-          l.z = tf32_rna(v.z - __uint_as_float(h.z));
-          l.w = tf32_rna(v.w - __uint_as_float(h.w));
+          l.x = __float_as_uint(v.x - __uint_as_float(h.x));
+          l.y = __float_as_uint(v.y - __uint_as_float(h.y));
+          l.z = __float_as_uint(v.z - __uint_as_float(h.z));
+          l.w = __float_as_uint(v.w - __uint_as_float(h.w));
           reinterpret_cast<uint4*>(hi)[e] = h;
           reinterpret_cast<uint4*>(lo)[e] = l;
         }
@@ -208,18 +214,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(cvt_bar(s));
     }
-    // ---- epilogue: TMEM -> registers -> global ----
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+  }
+
+  // ===================== epilogue (all 8 warps) =====================
+  // TMEM -> registers -> padded shared tile (conflict-free, reuses the now idle stage buffers)
+  // -> fully coalesced 512-byte row stores with bias / accumulate / de-interleave.
+  {
+    constexpr int CS = TBN + 4;  // padded row stride (floats): 16-byte lanes of 8 rows cover all 32 banks
+    float* csm = reinterpret_cast<float*>(smem_gen);
+    const int q = warp & 3;      // TMEM lane quarter this warp may access
+    const int half = warp >> 2;  // which 64 accumulator columns (warps 8+ only take part in the row stores)
     if (nkb > 0) {
       mbar_wait(acc_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const int m = m0 + q * 32 + lane;
 #pragma unroll 1
-    for (int cc = 0; cc < TBN / 32; ++cc) {
+    for (int cc = 0; cc < (half < 2 ? 2 : 0); ++cc) {
       uint32_t r[32];
+      const int col0 = half * 64 + cc * 32;
       if (nkb > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -236,28 +250,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (m < p.M) {
+      float* dst = csm + (size_t)(q * 32 + lane) * CS + col0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = n0 + cc * 32 + j * 4;
-          if (n >= p.N) continue;  // N % 4 == 0 is a precondition of this path
-          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          if (p.partial) {
-            *reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M + m) * p.N + n) = v;
-          } else {
-            if (p.bias) {
-              const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            }
-            const int row = p.deint_H > 0 ? ((m & 3) * p.deint_H + (m >> 2)) : m;
-            float4* o = reinterpret_cast<float4*>(p.c + (long long)row * p.ldc + n);
-            if (p.accumulate) {
-              const float4 old = *o;
-              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-            }
-            *o = v;
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const int n = n0 + lane * 4;
+    if (n < p.N) {  // N % 4 == 0 is a precondition of this path
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias && !p.partial) bias4 = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll 4
+      for (int rr = warp; rr < TBM; rr += TC_THREADS / 32) {
+        const int m = m0 + rr;
+        if (m >= p.M) break;
+        float4 v = *reinterpret_cast<const float4*>(csm + (size_t)rr * CS + lane * 4);
+        if (p.partial) {
+          *reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * p.M + m) * p.N + n) = v;
+        } else {
+          v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+          const int row = p.deint_H > 0 ? ((m & 3) * p.deint_H + (m >> 2)) : m;
+          float4* o = reinterpret_cast<float4*>(p.c + (long long)row * p.ldc + n);
+          if (p.accumulate) {
+            const float4 old = *o;
+            v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
           }
+          *o = v;
         }
       }
     }
@@ -387,7 +406,7 @@ int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStre
   dim3 grid((g.N + TBN - 1) / TBN, (g.M + TBM - 1) / TBM, zdim);
   ProfScope prof(PROF_GEMM, stream);
   count_launch(zdim > 1 ? 2 : 1);
-  gemm_tc_kernel<<<grid, 256, SMEM_BYTES, stream>>>(ma, mb, p);
+  gemm_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES, stream>>>(ma, mb, p);
   MRG_CUDA_CHECK(cudaGetLastError());
   if (zdim > 1) {
     const long long total = (long long)g.M * g.N;

@@ -148,19 +148,29 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnArgs a) {
   }
 }
 
-__global__ void ln_param_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int nblocks, int H) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * H) return;
+// 32 columns per CTA, 8 slices of the partial blocks per column, fixed-order tree: deterministic
+__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial,
+                                                              float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, int nblocks, int H) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);  // column in [0, 2H)
+  const int part = threadIdx.x >> 5;
   const int which = c / H, col = c % H;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 2 + which) * H + col];
-  (which == 0 ? dgamma : dbeta)[col] = s;
+  if (c < 2 * H)
+    for (int b = part; b < nblocks; b += 8) s += partial[((size_t)b * 2 + which) * H + col];
+  red[part][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (part == 0 && c < 2 * H) {
+    float t = red[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) t += red[w][threadIdx.x];
+    (which == 0 ? dgamma : dbeta)[col] = t;
+  }
 }
 
 static int ln_grid(long long rows) {
   long long blocks = (rows + 7) / 8;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -223,7 +233,7 @@ extern "C" int mrg_residual_layernorm_backward(const float* dout, long long d_s0
   else if (H == 256) ln_bwd_kernel<2><<<grid, 256, 0, stream>>>(a);
   else ln_bwd_kernel<4><<<grid, 256, 0, stream>>>(a);
   MRG_CUDA_CHECK(cudaGetLastError());
-  ln_param_reduce_kernel<<<(2 * H + 127) / 128, 128, 0, stream>>>(a.partial, dgamma, dbeta, grid, H);
+  ln_param_reduce_kernel<<<(2 * H + 31) / 32, 256, 0, stream>>>(a.partial, dgamma, dbeta, grid, H);
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

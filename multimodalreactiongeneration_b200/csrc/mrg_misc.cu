@@ -47,16 +47,22 @@ struct PackArgs {
   const float* w_ih[2];
   const float* b_ih[2];
   const float* b_hh[2];
+  const float* w_hh[2];
 };
 
-__global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __restrict__ bias_pack, int I,
-                            int H) {
+__global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __restrict__ bias_pack,
+                            float* __restrict__ whh_pack, int I, int H) {
   const int d = blockIdx.y;
   const int row = blockIdx.x;  // packed row j*4+g
   const int j = row >> 2, g = row & 3;
   const float* src = p.w_ih[d] + (size_t)(g * H + j) * I;
   float* dst = w_pack + ((size_t)d * 4 * H + row) * I;
   for (int i = threadIdx.x; i < I; i += blockDim.x) dst[i] = src[i];
+  if (whh_pack != nullptr) {  // single-step path: h0 * W_hh^T is a second projection GEMM
+    const float* hs = p.w_hh[d] + (size_t)(g * H + j) * H;
+    float* hd = whh_pack + ((size_t)d * 4 * H + row) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) hd[i] = hs[i];
+  }
   if (threadIdx.x == 0 && bias_pack != nullptr) {
     float b = 0.f;
     if (p.b_ih[d]) b += p.b_ih[d][g * H + j];
@@ -65,16 +71,17 @@ __global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __res
   }
 }
 
-int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, int I, int H, int D,
-                 cudaStream_t stream) {
+int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, float* whh_pack, int I, int H,
+                 int D, cudaStream_t stream) {
   PackArgs p;
   for (int d = 0; d < 2; ++d) {
+    p.w_hh[d] = d < D ? w[d].w_hh : nullptr;
     p.w_ih[d] = d < D ? w[d].w_ih : nullptr;
     p.b_ih[d] = d < D ? w[d].b_ih : nullptr;
     p.b_hh[d] = d < D ? w[d].b_hh : nullptr;
   }
   dim3 grid(4 * H, D);
-  pack_kernel<<<grid, 128, 0, stream>>>(p, w_pack, bias_pack, I, H);
+  pack_kernel<<<grid, 128, 0, stream>>>(p, w_pack, bias_pack, whh_pack, I, H);
   MRG_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return 0;
@@ -106,7 +113,7 @@ int colsum_deinterleave(const float* part, float* db, int B, int H, int accumula
 // reference's rollout.  One thread per (direction, row, unit).
 // ---------------------------------------------------------------------------------------------
 __global__ void cell_zero_fwd_kernel(float* __restrict__ gates, float* __restrict__ y_ext,
-                                     float* __restrict__ c_ext, int B, int H, int D, int train) {
+                                     float* __restrict__ c_ext, int B, int H, int D, int train, int has_state) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_dir = (long long)B * H;
   if (idx >= per_dir * D) return;
@@ -115,9 +122,11 @@ __global__ void cell_zero_fwd_kernel(float* __restrict__ gates, float* __restric
   float4* gp = reinterpret_cast<float4*>(gates) + idx;                // [D][1][B][H] float4
   const float4 x = *gp;
   const float gi = sigmoid_acc(x.x), gf = sigmoid_acc(x.y), gg = tanhf(x.z), go = sigmoid_acc(x.w);
-  const float c = gi * gg;
-  const float h = go * tanhf(c);
   const long long out = (long long)d * 2 * per_dir + (d == 0 ? per_dir : 0) + r;  // dir0: slot 1, dir1: slot 0
+  const long long init = (long long)d * 2 * per_dir + (d == 0 ? 0 : per_dir) + r; // the other slot holds c0
+  float c = gi * gg;
+  if (has_state) c = fmaf(gf, c_ext[init], c);  // carried state: the h0 * W_hh term is already in `gates`
+  const float h = go * tanhf(c);
   y_ext[out] = h;
   c_ext[out] = c;
   if (train) *gp = make_float4(gi, gf, gg, go);
@@ -147,11 +156,12 @@ __global__ void cell_zero_bwd_kernel(float* __restrict__ gates, const float* __r
 }
 
 int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
-                            cudaStream_t stream) {
+                            int has_state, cudaStream_t stream) {
   const long long n = (long long)B * H * D;
   ProfScope prof(PROF_REC_FWD, stream);
   count_launch();
-  cell_zero_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gates, y_ext, c_ext, B, H, D, train);
+  cell_zero_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gates, y_ext, c_ext, B, H, D, train,
+                                                                        has_state);
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -57,7 +57,13 @@ def build_optimizer(model: nn.Module):
     """``configure_optimizers`` of the reference models returns {"optimizer", "lr_scheduler": {...}}."""
     cfg = model.configure_optimizers()
     sched = cfg.get("lr_scheduler", {}).get("scheduler") if isinstance(cfg, dict) else None
-    return cfg["optimizer"], sched
+    opt = cfg["optimizer"]
+    on_gpu = any(p.is_cuda for g in opt.param_groups for p in g["params"])
+    if on_gpu:  # keep the step counters on the device from the first step on (CUDA-graph capturable)
+        for group in opt.param_groups:
+            if "capturable" in group:
+                group["capturable"] = True
+    return opt, sched
 
 
 class Trainer:
@@ -83,6 +89,41 @@ class Trainer:
         self.optimizer.step()
         self.global_step += 1
         return loss.detach()
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole step (zero bucket -> fwd -> bwd -> all-reduce -> optimizer).
+    # The step launches several hundred small kernels; replaying one captured graph removes the host
+    # enqueue time (~19 ms at the bench shape) from the critical path.  Shapes must be static: the
+    # batch is copied into fixed device buffers first.  Not usable for steps with host reads inside
+    # (the wavefront rollout reads the wave sizes once per step).
+    # ------------------------------------------------------------------------------------------
+    def enable_cuda_graph(self, example_batch, warmup: int = 3) -> None:
+        assert all(torch.is_tensor(t) and t.is_cuda for t in example_batch), "graphed step takes CUDA tensors"
+        for group in self.optimizer.param_groups:      # the learning rate is read from device memory
+            if not torch.is_tensor(group["lr"]):
+                group["lr"] = torch.tensor(float(group["lr"]), dtype=torch.float32,
+                                           device=example_batch[0].device)
+        self._static_batch = tuple(torch.empty_like(t) for t in example_batch)
+        for dst, src in zip(self._static_batch, example_batch):
+            dst.copy_(src)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._static_loss = self.train_step(self._static_batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.train_step(self._static_batch)
+        self.global_step -= 1  # the capture pass did not execute
+
+    def train_step_graphed(self, batch) -> torch.Tensor:
+        for dst, src in zip(self._static_batch, batch):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.global_step += 1
+        return self._static_loss
 
     @torch.no_grad()
     def validate(self, batches: Iterable) -> float:

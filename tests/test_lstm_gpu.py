@@ -42,6 +42,9 @@ CASES = [
     (32, 32, 1, False, 3, 9, True),        # golden-fixture sizes -> generic kernels
     (10, 16, 2, True, 3, 7, True),
     (256, 256, 1, False, 130, 5, False),   # more row slices than one wave of clusters
+    (128, 128, 2, False, 16, 1, True),     # single step with carried state: GEMM + pointwise cell (streaming)
+    (256, 256, 1, False, 70, 1, True),
+    (12, 16, 1, True, 3, 1, True),
 ]
 
 
