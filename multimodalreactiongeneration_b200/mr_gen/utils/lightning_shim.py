@@ -18,8 +18,10 @@ class LightningModule(nn.Module):
             return torch.device("cpu")
 
     def log(self, name, value, **_):
-        self.logged[name] = value
+        # detached: a logged loss must not keep the step's autograd graph alive
+        self.logged[name] = value.detach() if torch.is_tensor(value) else value
 
     def log_dict(self, values, **_):
         if isinstance(values, dict):
-            self.logged.update(values)
+            for k, v in values.items():
+                self.log(k, v)

@@ -214,3 +214,28 @@ def test_wavefront_rollout_equals_stepwise_loop_with_philox_masks():
     assert rel_err(f1, f0) <= 5e-5
     for k in g0:
         assert rel_l2(g1[k], g0[k]) <= GRAD_TOL, k
+
+
+def test_streaming_generator_matches_free_running_prediction():
+    """Frame-by-frame generation with carried sampler state == prediction(full_generation=True)."""
+    from multimodalreactiongeneration_b200.mr_gen.configs import lstm_with_sampling_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstm_with_sampling.lstm_with_sample import LSTMwithSample
+    from multimodalreactiongeneration_b200.mr_gen.model.lstm_with_sampling.streaming import StreamingGenerator
+    B, T, lead, ratio = 6, 9, 2, 2
+    torch.manual_seed(1)
+    m = LSTMwithSample(*lstm_with_sampling_cfg(scheduled=False, ratio=ratio)).cuda().eval()
+    g = torch.Generator().manual_seed(2)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    batch = [(r(B, T * ratio, 80), None), (r(B, T, 6), None), (r(B, T, 6), None), (r(B, lead * ratio, 80), None),
+             (r(B, lead, 6), None), (r(B, lead, 6), None), (r(B, T, 6), None)]
+    with torch.no_grad():
+        want, _ = m.prediction(batch, full_generation=True)
+    for graph in (False, True):
+        gen = StreamingGenerator(m, B, use_cuda_graph=graph)
+        gen.reset(batch[3][0])
+        got = []
+        for t in range(T):
+            prev = batch[2][0][:, 0] if t == 0 else None       # the rollout starts from motion_s[0]
+            got.append(gen.step(batch[0][0][:, t * ratio:(t + 1) * ratio], batch[1][0][:, t], prev).clone())
+        got = torch.stack(got, dim=1)
+        assert rel_err(got, want) <= 5e-5, graph
