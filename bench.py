@@ -245,6 +245,13 @@ def run_ours(args):
     dom_ms, dom_n = (bwd_ms, bwd_n) if dom == "rec_bwd" else (fwd_ms, fwd_n)
     per_frame = BYTES_BWD_PER_FRAME if dom == "rec_bwd" else BYTES_FWD_PER_FRAME
     avg_ms = dom_ms / max(1, dom_n)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture
+        with open(tpath) as fh:
+            t = json.load(fh).get(dom)
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     achieved = frames_per_launch * per_frame / (avg_ms * 1e-3) / 1e9
     line = {
         "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -260,7 +267,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": f"{dom}_cluster_kernel<256>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": frames_per_launch * per_frame,
                      "note": "latency-bound recurrence: T dependent steps per launch; see latency_us_per_timestep"},
         "latency_us_per_timestep": {"rec_fwd": 1e3 * fwd_ms / max(1, fwd_n) / T_FRAMES,

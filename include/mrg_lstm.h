@@ -51,6 +51,9 @@ extern "C" {
 #define MRG_F_GENERIC_REC  2   /* force the generic (non-cluster) recurrent kernels             */
 #define MRG_F_SIMT_GEMM    4   /* force the SIMT fp32 GEMM instead of the tcgen05 3xTF32 GEMM   */
 #define MRG_F_ACCUMULATE   8   /* backward: add into dw_ih / dw_hh / db instead of overwriting  */
+#define MRG_F_TF32        32   /* reduced-precision mode: the projection GEMMs run ONE tf32 tensor-core
+                                  pass (10-bit mantissa, >= bf16 precision) instead of the 3-pass
+                                  fp32-grade split; the recurrence itself stays fp32               */
 #define MRG_F_ZERO_STATE  16   /* caller guarantees h0 = c0 = 0 (hx=None): with T == 1 the layer is a
                                   pointwise cell on the projection (no recurrence, W_hh inert) — the
                                   stateless predictor steps of the lstm_with_sampling rollout       */

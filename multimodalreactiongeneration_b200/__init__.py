@@ -9,6 +9,7 @@ Public surface:
 There is no CPU fallback: calling the LSTM path without the compiled extension or without a
 compute-capability-10.x device raises.
 """
-from .lstm import B200LSTM, lstm_layer  # noqa: F401
+from .lstm import B200LSTM, lstm_layer, set_precision  # noqa: F401
+from .linear import B200Linear  # noqa: F401
 
-__all__ = ["B200LSTM", "lstm_layer"]
+__all__ = ["B200LSTM", "B200Linear", "lstm_layer", "set_precision"]

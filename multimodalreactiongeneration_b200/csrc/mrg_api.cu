@@ -10,7 +10,9 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K);
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int run_gemm(const GemmArgs& g, void* ws, size_t ws_bytes, int flags, cudaStream_t stream) {
+static int run_gemm(const GemmArgs& g_in, void* ws, size_t ws_bytes, int flags, cudaStream_t stream) {
+  GemmArgs g = g_in;
+  g.single_pass = (flags & MRG_F_TF32) ? 1 : 0;
 #ifdef MRG_HAVE_TC_GEMM
   if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) return gemm_tc(g, ws, ws_bytes, stream);
 #endif

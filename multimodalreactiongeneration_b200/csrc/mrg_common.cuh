@@ -154,6 +154,7 @@ struct GemmArgs {
   int M, N, K;
   int accumulate;      // C += result
   int row_deinterleave_H;  // >0: output row m=(j*4+g) is stored at row g*H+j (gate de-interleave)
+  int single_pass;         // tensor-core path only: one tf32 pass (MRG_F_TF32) instead of 3xTF32
 };
 
 int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -38,6 +38,7 @@ struct TcParams {
   int accumulate;
   int deint_H;
   float* partial;       // split-K partial sums [gridDim.z][M][N] or nullptr
+  int single_pass;      // MRG_F_TF32: hi*hi only
 };
 
 // hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the low 13
@@ -176,9 +177,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint64_t dal = make_smem_desc(a_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
           const uint64_t dbh = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
           const uint64_t dbl = make_smem_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          if (p.single_pass) {
+            umma_tf32(tmem_base, dah, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          } else {
+            umma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          }
         }
         umma_commit(empty_bar(s));  // stage reusable once these MMAs have read it
       }
@@ -207,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           l.z = __float_as_uint(v.z - __uint_as_float(h.z));
           l.w = __float_as_uint(v.w - __uint_as_float(h.w));
           reinterpret_cast<uint4*>(hi)[e] = h;
-          reinterpret_cast<uint4*>(lo)[e] = l;
+          if (!p.single_pass) reinterpret_cast<uint4*>(lo)[e] = l;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
@@ -395,6 +400,7 @@ int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStre
   const int zdim = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.c = g.c; p.ldc = g.ldc; p.bias = g.bias; p.accumulate = g.accumulate; p.deint_H = g.row_deinterleave_H;
   p.partial = nullptr;
+  p.single_pass = g.single_pass;
   if (zdim > 1) {
     const size_t need = (size_t)zdim * g.M * g.N * sizeof(float);
     if (workspace == nullptr || workspace_bytes < need) {
