@@ -15,79 +15,9 @@
 // contiguous, used by the weight-gradient GEMMs dW = dG^T X): the raw tile is position-preserving under
 // the hi/lo split, so only the TMA box + swizzle mode (128B vs 128B_ATOM_32B), the shared-memory
 // descriptor (layout type, LBO/SBO, K advance) and the major bits of the instruction descriptor change.
-#include <cuda.h>
-
-#include "mrg_common.cuh"
+#include "mrg_tc_common.cuh"
 
 namespace mrg {
-
-constexpr int TBM = 128, TBN = 128, TBK = 32;
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = TBM * TBK * 4;                 // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;               // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-
-struct TcParams {
-  int M, N, K;
-  int a_mn, b_mn;       // 1 = MN-major operand
-  int kb_total;         // ceil(K / 32)
-  int kb_per_split;
-  float* c;
-  long long ldc;
-  const float* bias;
-  int accumulate;
-  int deint_H;
-  float* partial;       // split-K partial sums [gridDim.z][M][N] or nullptr
-  int single_pass;      // MRG_F_TF32: hi*hi only
-};
-
-// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the low 13
-// bits) with two full-rate integer ops instead of cvt.rna.tf32.f32 (a quarter-rate conversion-pipe op).
-// lo = x - hi is exact in fp32 and is handed to the tensor core as is: it ignores the low 13 mantissa
-// bits of a tf32 operand, an error of 2^-10 relative to lo, i.e. 2^-21 relative to x.
-__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).  layout_type: 2 =
-// SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B — the only layout the tensor core accepts for
-// MN-major 32-bit operands (swizzle atom = 4 k-rows x 128 B, 32-byte swizzle granularity).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
 
 constexpr int CVT_WARPS = 8;
 constexpr int TC_THREADS = 128 + CVT_WARPS * 32;
