@@ -39,6 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("MRG_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DMRG_REC_TRACE (developer builds)
     objs = []
     procs = []
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)

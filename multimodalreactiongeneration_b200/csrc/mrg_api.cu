@@ -1,6 +1,8 @@
 // C-ABI entry points (include/mrg_lstm.h): orchestration of pack -> projection GEMM -> recurrent
 // kernel for the forward, and recurrent BPTT kernel -> dX / dW GEMMs -> bias column sums for the
 // backward.  Everything is queued on the caller's stream; nothing synchronises.
+#include <cstdlib>
+
 #include "mrg_common.cuh"
 
 namespace mrg {
@@ -56,8 +58,8 @@ extern "C" int mrg_device_info(int* sm_count, int* max_clusters_h256, int* max_c
   if (sm_count) *sm_count = p.multiProcessorCount;
   if (cc_major) *cc_major = p.major;
   if (cc_minor) *cc_minor = p.minor;
-  if (max_clusters_h256) *max_clusters_h256 = max_active_clusters(256);
-  if (max_clusters_h128) *max_clusters_h128 = max_active_clusters(128);
+  if (max_clusters_h256) *max_clusters_h256 = max_active_clusters2(256);
+  if (max_clusters_h128) *max_clusters_h128 = max_active_clusters2(128);
   return 0;
 }
 
@@ -152,6 +154,8 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   r.y_ext = y_ext; r.c_ext = c_ext;
   r.T = T; r.B = B; r.H = H; r.D = D;
   r.train = (flags & MRG_F_TRAIN) ? 1 : 0;
+  r.trace = debug_trace_buffer();
+  if (!(flags & (MRG_F_GENERIC_REC | MRG_F_REC_V1)) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
   if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) return rec_forward_cluster(r, stream);
   return rec_forward_generic(r, stream);
 }
@@ -193,6 +197,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   bool pointwise = (T == 1) && (flags & MRG_F_ZERO_STATE);
   for (int d = 0; d < D; ++d) pointwise = pointwise && !g[d].dh0 && !g[d].dc0;
   if (pointwise) e = cell_zero_state_backward(gates, c_ext, dy, dh_n, dc_n, db_part, B, H, D, stream);
+  else if (!(flags & (MRG_F_GENERIC_REC | MRG_F_REC_V1)) && rec2_supported(H)) e = rec_backward_cluster2(r, stream);
   else if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) e = rec_backward_cluster(r, stream);
   else e = rec_backward_generic(r, stream);
   if (e) return e;

@@ -93,6 +93,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
                    remote_addr),
@@ -107,6 +116,82 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint
       "r"(__float_as_uint(v.w)), "r"(remote_bar)
       : "memory");
 }
+
+// Predicated forms (one instruction under a predicate instead of a branch around it): the software-pipelined
+// recurrent kernels need their whole iteration in ONE basic block so that ptxas can interleave the
+// latency-bound tail of one chunk with the FFMA2 block of the next.
+__device__ __forceinline__ void st_async_v4_if(bool p, uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %6, 0;\n"
+      "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n}" ::"r"(
+          remote_addr),
+      "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+      "r"(__float_as_uint(v.w)), "r"(remote_bar), "r"((uint32_t)p)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_v4_if(bool p, float* addr, float4 v) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %5, 0;\n@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n}" ::"l"(addr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)p)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_f32_if(bool p, float* addr, float v) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p st.global.f32 [%0], %1;\n}" ::"l"(addr), "f"(v),
+               "r"((uint32_t)p)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16_if(bool p, uint32_t dst, const void* src) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.cg.shared.global [%0], [%1], 16;\n}" ::"r"(dst),
+               "l"(src), "r"((uint32_t)p)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(bool p, uint32_t dst, const void* src) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p cp.async.ca.shared.global [%0], [%1], 4;\n}" ::"r"(dst),
+               "l"(src), "r"((uint32_t)p)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(bool p, uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %2, 0;\n@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}" ::"r"(bar),
+               "r"(bytes), "r"((uint32_t)p)
+               : "memory");
+}
+
+// Gate non-linearities of the second-generation kernels: ex2.approx.ftz / rcp.approx.ftz directly (2 MUFU + 2-3
+// FP32 ops, no denormal range fix-up): |error| <= ~2e-7 absolute, the same order as one fp32 rounding of the
+// pre-activation; saturates correctly (ex2 -> inf gives rcp -> 0).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(x * 2.8853900817779268f)), 1.0f);
+}
+
+// Developer-only event trace of the recurrent kernels (-DMRG_REC_TRACE): lane 0 of every warp of CTA 0 appends
+// (clock, warp, event, chunk, step) records to a global buffer set with mrg_debug_set_trace().
+#ifdef MRG_REC_TRACE
+// 1024 (clock, packed event) slots per warp, plain stores (no atomics: the trace must not stall the warp)
+__device__ __forceinline__ void rec_trace(unsigned long long* buf, unsigned& n, int evt, int ch, int step) {
+  if (buf && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && n < 1024u) {
+    unsigned long long* p = buf + ((size_t)(threadIdx.x >> 5) * 1024 + n) * 2;
+    p[0] = clock64();
+    p[1] = ((unsigned long long)(threadIdx.x >> 5) << 48) | ((unsigned long long)evt << 32) |
+           ((unsigned long long)ch << 16) | (unsigned long long)step;
+    ++n;
+  }
+}
+#define REC_TRACE_DECL unsigned trace_n = 0;
+#define REC_TRACE(evt, ch, step) rec_trace(a.trace, trace_n, evt, ch, step)
+#else
+#define REC_TRACE_DECL
+#define REC_TRACE(evt, ch, step)
+#endif
 
 // packed fp32x2 FMA (Blackwell FFMA2): d = a * b + d on both halves
 __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
@@ -170,7 +255,9 @@ struct RecArgs {
   float* c_ext;        // [D][T+1][B][H]
   int T, B, H, D;
   int train;
+  unsigned long long* trace;  // developer event trace (-DMRG_REC_TRACE builds), else nullptr
 };
+unsigned long long* debug_trace_buffer();
 int rec_forward_generic(const RecArgs& a, cudaStream_t stream);
 int rec_forward_cluster(const RecArgs& a, cudaStream_t stream);  // H in {128, 256}
 bool rec_cluster_supported(int H);
@@ -190,6 +277,14 @@ struct RecBwdArgs {
 };
 int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream);
+// second-generation cluster kernels (chunk-pipelined, H in {128, 256}); the first generation stays
+// selectable with MRG_F_REC_V1 for A/B measurements
+int rec_forward_cluster2(const RecArgs& a, cudaStream_t stream);
+int rec_backward_cluster2(const RecBwdArgs& a, cudaStream_t stream);
+bool rec2_supported(int H);
+int max_active_clusters2(int H);
+int rec2_max_chunks(int H, int rbc);
+void pick_partition2(int H, int B, int D, int* slices_out, int* nch_out, int* rbc_out);
 
 int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
                             int has_state, cudaStream_t stream);

@@ -244,3 +244,13 @@ extern "C" int mrg_profile_read(float* ms, int* n) {
 
 extern "C" int mrg_version(void) { return MRG_VERSION; }
 extern "C" const char* mrg_last_error_string(void) { return mrg::last_error(); }
+
+namespace mrg {
+static unsigned long long* g_trace_buf = nullptr;
+unsigned long long* debug_trace_buffer() { return g_trace_buf; }
+}  // namespace mrg
+// developer hook: device buffer of 1 + 2*65535 uint64 that -DMRG_REC_TRACE builds of the recurrent kernels fill
+extern "C" int mrg_debug_set_trace(unsigned long long* buf) {
+  mrg::g_trace_buf = buf;
+  return 0;
+}

@@ -45,6 +45,14 @@ CASES = [
     (128, 128, 2, False, 16, 1, True),     # single step with carried state: GEMM + pointwise cell (streaming)
     (256, 256, 1, False, 70, 1, True),
     (12, 16, 1, True, 3, 1, True),
+    # second-generation cluster kernels: chunk pipeline with 1..8 chunks, ragged chunks, several waves
+    (256, 256, 1, False, 256, 6, True),    # 17-18 rows per cluster -> 5 chunks of 3-4 rows
+    (256, 256, 1, True, 31, 9, True),      # two directions share the clusters: 4-5 rows, chunks of 2-3
+    (128, 128, 1, False, 100, 8, True),    # H=128: clusters of 4 CTAs
+    (256, 256, 1, False, 1, 11, True),     # one row: a single chunk, no pipelining
+    (256, 256, 1, False, 2, 11, False),
+    (256, 256, 1, False, 17, 4, True),     # clusters with 1 and 2 rows (an empty chunk in some)
+    (256, 256, 1, False, 600, 3, True),    # more than 32 rows per co-resident cluster: several waves
 ]
 
 
@@ -114,6 +122,29 @@ def test_cluster_and_generic_kernels_agree():
         y, h, c = lstm_layer(xx, ws, H, 1, flags=flags)
         (y.sin().sum() + c.sum()).backward()
         outs.append((y, h, c, xx.grad, *[t.grad for t in ws]))
+    for a, b in zip(*outs):
+        assert rel_err(a, b) <= 2e-5
+
+
+@pytest.mark.parametrize("B,H", [(64, 256), (23, 128)])
+def test_first_and_second_generation_cluster_kernels_agree(B, H):
+    from multimodalreactiongeneration_b200 import lstm_layer, _cabi
+    torch.manual_seed(4)
+    T, I = 19, 128
+    x = torch.randn(T, B, I, device="cuda")
+    k = 1.0 / np.sqrt(H)
+    w = [torch.empty(4 * H, I, device="cuda").uniform_(-k, k), torch.empty(4 * H, H, device="cuda").uniform_(-k, k),
+         torch.empty(4 * H, device="cuda").uniform_(-k, k), torch.empty(4 * H, device="cuda").uniform_(-k, k)]
+    h0 = torch.randn(1, B, H, device="cuda") * 0.5
+    c0 = torch.randn(1, B, H, device="cuda") * 0.5
+    outs = []
+    for flags in (0, _cabi.F_REC_V1):
+        ws = [t.clone().requires_grad_(True) for t in w]
+        xx = x.clone().requires_grad_(True)
+        hh, cc = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+        y, h, c = lstm_layer(xx, ws, H, 1, h0=hh, c0=cc, flags=flags)
+        (y.sin().sum() + c.sum() + h.cos().sum()).backward()
+        outs.append((y, h, c, xx.grad, hh.grad, cc.grad, *[t.grad for t in ws]))
     for a, b in zip(*outs):
         assert rel_err(a, b) <= 2e-5
 
