@@ -137,6 +137,25 @@ int mrg_residual_layernorm_backward(const float* dout, long long d_s0, long long
 int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared, uint8_t* out,
                     void* stream);
 
+/* out[N] (+)= column sums of x[M][N] (N % 4 == 0, x 16-byte aligned): the bias gradient of the Linear layers next
+ * to the LSTMs (LSTMModule.mixer, the bottleneck FFN, embed / projection layers).  Deterministic two-pass sum. */
+size_t mrg_colsum_workspace_bytes(int M, int N);
+int mrg_colsum(const float* x, float* out, int M, int N, int accumulate, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* Optimizer step of the training loop (mr_gen/model/simple_lstm/simple_lstm.py:193-221 builds torch.optim.AdamW):
+ * decoupled-weight-decay Adam over FLAT fp32 buckets p / g / m / v of n floats (n % 4 == 0), torch.optim.AdamW
+ * arithmetic.  state[3] (device) = {step count, 1/(1-b1^step), 1/sqrt(1-b2^step)}, advanced by the call itself so a
+ * captured CUDA graph keeps counting.  lr is read from lr_dev when non-NULL.  g is scaled by grad_scale first
+ * (1/world_size after the all-reduce) and cleared afterwards when zero_grad != 0. */
+int mrg_adamw_flat(float* p, float* g, float* m, float* v, size_t n, const float* lr_dev, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float* state, float grad_scale, int zero_grad,
+                   void* stream);
+
+/* Developer hook: device buffer of 16*1024*2 uint64 that -DMRG_REC_TRACE builds of the recurrent kernels fill
+ * with (clock, event) records; NULL disables.  No effect in regular builds. */
+int mrg_debug_set_trace(unsigned long long* buf);
+
 /* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded,
  * and CUDA-event timing of the recurrent / GEMM launches on their own stream.  mrg_profile_read fills
  * ms[3], n[3] for {recurrent forward, recurrent backward, GEMM} and resets the record. */

@@ -11,5 +11,6 @@ compute-capability-10.x device raises.
 """
 from .lstm import B200LSTM, lstm_layer, set_precision  # noqa: F401
 from .linear import B200Linear  # noqa: F401
+from .attention import B200MultiheadAttention  # noqa: F401
 
-__all__ = ["B200LSTM", "B200Linear", "lstm_layer", "set_precision"]
+__all__ = ["B200LSTM", "B200Linear", "B200MultiheadAttention", "lstm_layer", "set_precision"]

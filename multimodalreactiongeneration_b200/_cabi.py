@@ -15,7 +15,7 @@ EXPORTS = (
     "mrg_lstm_layer_forward", "mrg_lstm_layer_backward", "mrg_gemm_nt", "mrg_philox_mask",
     "mrg_launch_count", "mrg_profile_enable", "mrg_profile_read", "mrg_gemm_strided",
     "mrg_gemm_workspace_bytes", "mrg_layernorm_workspace_bytes", "mrg_residual_layernorm_forward",
-    "mrg_residual_layernorm_backward",
+    "mrg_residual_layernorm_backward", "mrg_adamw_flat", "mrg_debug_set_trace", "mrg_colsum", "mrg_colsum_workspace_bytes",
 )
 
 
@@ -81,6 +81,14 @@ def lib() -> ctypes.CDLL:
                                                   c_void_p, c_void_p, c_void_p, LL, LL, c_void_p, c_void_p, c_void_p,
                                                   c_size_t, c_int, c_int, c_int, c_void_p]
     L.mrg_residual_layernorm_backward.restype = c_int
+    L.mrg_adamw_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_float,
+                                 c_float, c_float, c_void_p, c_float, c_int, c_void_p]
+    L.mrg_adamw_flat.restype = c_int
+    L.mrg_debug_set_trace.argtypes = [c_void_p]
+    L.mrg_colsum_workspace_bytes.argtypes = [c_int, c_int]
+    L.mrg_colsum_workspace_bytes.restype = c_size_t
+    L.mrg_colsum.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]
+    L.mrg_colsum.restype = c_int
     L.mrg_launch_count.restype = ctypes.c_ulonglong
     L.mrg_profile_enable.argtypes = [c_int]
     L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]

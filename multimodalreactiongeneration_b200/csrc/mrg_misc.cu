@@ -245,6 +245,147 @@ extern "C" int mrg_profile_read(float* ms, int* n) {
 extern "C" int mrg_version(void) { return MRG_VERSION; }
 extern "C" const char* mrg_last_error_string(void) { return mrg::last_error(); }
 
+// ---------------------------------------------------------------------------------------------------------
+// Column sums out[n] = sum_m x[m][n] — the bias gradient of the Linear layers on the [B*T, N] stream
+// (db = dy^T 1).  HBM-bound, deterministic: pass 1 sums slabs of COLSUM_ROWS rows with coalesced 16-byte
+// loads into partial[slab][N], pass 2 adds the slabs in a fixed order.
+// ---------------------------------------------------------------------------------------------------------
+namespace mrg {
+constexpr int COLSUM_ROWS = 128;
+__global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restrict__ x, float* __restrict__ partial,
+                                                          int M, int N) {
+  // blockDim = 256: 64 column quads x 4 row phases; grid = (ceil(N/256), slabs)
+  const int cq = threadIdx.x & 63, rp = threadIdx.x >> 6;
+  const int n = blockIdx.x * 256 + cq * 4;
+  const int m0 = blockIdx.y * COLSUM_ROWS;
+  const int m1 = min(M, m0 + COLSUM_ROWS);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n + 3 < N) {
+    for (int m = m0 + rp; m < m1; m += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * N + n));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  } else {
+    for (int m = m0 + rp; m < m1; m += 4) {
+      const float* r = x + (size_t)m * N;
+      if (n < N) acc.x += r[n];
+      if (n + 1 < N) acc.y += r[n + 1];
+      if (n + 2 < N) acc.z += r[n + 2];
+    }
+  }
+  __shared__ float4 red[4][64];
+  red[rp][cq] = acc;
+  __syncthreads();
+  if (rp == 0) {
+    float4 s = red[0][cq];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { s.x += red[i][cq].x; s.y += red[i][cq].y; s.z += red[i][cq].z; s.w += red[i][cq].w; }
+    float* o = partial + (size_t)blockIdx.y * N;
+    if (n < N) o[n] = s.x;
+    if (n + 1 < N) o[n + 1] = s.y;
+    if (n + 2 < N) o[n + 2] = s.z;
+    if (n + 3 < N) o[n + 3] = s.w;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int slabs, int N,
+                                    int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = accumulate ? out[n] : 0.f;
+  for (int i = 0; i < slabs; ++i) s += partial[(size_t)i * N + n];
+  out[n] = s;
+}
+}  // namespace mrg
+
+extern "C" size_t mrg_colsum_workspace_bytes(int M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return (size_t)((M + mrg::COLSUM_ROWS - 1) / mrg::COLSUM_ROWS) * N * sizeof(float);
+}
+
+extern "C" int mrg_colsum(const float* x, float* out, int M, int N, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MRG_REQUIRE(out && M >= 0 && N > 0 && (x || M == 0), "mrg_colsum: bad arguments");
+  MRG_REQUIRE(((uintptr_t)x & 15) == 0, "mrg_colsum: x must be 16-byte aligned");
+  if (M == 0) {
+    if (!accumulate) MRG_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), stream));
+    return 0;
+  }
+  if (workspace == nullptr || workspace_bytes < mrg_colsum_workspace_bytes(M, N)) {
+    mrg::set_error("mrg_colsum: workspace too small");
+    return MRG_E_WORKSPACE;
+  }
+  const int slabs = (M + mrg::COLSUM_ROWS - 1) / mrg::COLSUM_ROWS;
+  mrg::count_launch(2);
+  MRG_REQUIRE(N % 4 == 0, "mrg_colsum: N must be a multiple of 4 (16-byte aligned rows)");
+  mrg::colsum_slab_kernel<<<dim3((N + 255) / 256, slabs), 256, 0, stream>>>(x, (float*)workspace, M, N);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  mrg::colsum_final_kernel<<<(N + 255) / 256, 256, 0, stream>>>((const float*)workspace, out, slabs, N, accumulate);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Flat AdamW: the optimizer step of the trainer (reference: torch.optim.AdamW built in configure_optimizers,
+// mr_gen/model/simple_lstm/simple_lstm.py:193-221) as ONE streamed kernel over the flat parameter / gradient
+// buckets instead of ~230 foreach launches.  HBM-bound: 4 reads + 3 (4 with zero_grad) writes of 4 bytes per
+// parameter.  state = {step, 1/(1-b1^step), 1/sqrt(1-b2^step)} lives on the device so that a captured CUDA graph
+// advances the step count on every replay.
+// ---------------------------------------------------------------------------------------------------------
+namespace mrg {
+__global__ void adamw_state_kernel(float* state, float b1, float b2) {
+  const float step = state[0] + 1.0f;
+  state[0] = step;
+  state[1] = 1.0f / (1.0f - powf(b1, step));
+  state[2] = 1.0f / sqrtf(1.0f - powf(b2, step));
+}
+
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float4* __restrict__ p, float4* __restrict__ g,
+                                                         float4* __restrict__ m, float4* __restrict__ v,
+                                                         size_t n4, const float* __restrict__ lr_dev, float lr_host,
+                                                         float b1, float b2, float eps, float wd,
+                                                         const float* __restrict__ state, float gscale,
+                                                         int zero_grad) {
+  const float lr = lr_dev ? *lr_dev : lr_host;
+  const float step_size = lr * state[1];
+  const float inv_sqrt_bc2 = state[2];
+  const float decay = 1.0f - lr * wd;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = G[k] * gscale;
+      M[k] = M[k] + (gr - M[k]) * (1.0f - b1);
+      V[k] = V[k] * b2 + gr * gr * (1.0f - b2);
+      const float denom = sqrtf(V[k]) * inv_sqrt_bc2 + eps;
+      P[k] = P[k] * decay - step_size * (M[k] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (zero_grad) g[i] = zero;
+  }
+}
+}  // namespace mrg
+
+extern "C" int mrg_adamw_flat(float* p, float* g, float* m, float* v, size_t n, const float* lr_dev, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, float* state,
+                              float grad_scale, int zero_grad, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MRG_REQUIRE(p && g && m && v && state, "mrg_adamw_flat: null pointer");
+  MRG_REQUIRE(n % 4 == 0, "mrg_adamw_flat: the flat buckets must be padded to a multiple of 4 floats");
+  if (n == 0) return 0;
+  mrg::adamw_state_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  const size_t n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mrg::count_launch(2);
+  mrg::adamw_flat_kernel<<<blocks, 256, 0, stream>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, lr_dev, lr,
+                                                     beta1, beta2, eps, weight_decay, state, grad_scale, zero_grad);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 namespace mrg {
 static unsigned long long* g_trace_buf = nullptr;
 unsigned long long* debug_trace_buffer() { return g_trace_buf; }

@@ -25,6 +25,22 @@ def _gemm(a, a_sm, a_sk, b, b_sk, b_sn, bias, c, M, N, K, flags):
     _cabi.check(st, "mrg_gemm_strided")
 
 
+def _colsum(x2):
+    """Column sums of a contiguous [M, N] fp32 matrix (bias gradient) through the C-ABI; torch only for N % 4 != 0."""
+    M, N = x2.shape
+    if N % 4 != 0 or x2.data_ptr() % 16 != 0:
+        return x2.sum(dim=0)
+    L = _cabi.lib()
+    dev = x2.device
+    out = torch.empty(N, dtype=torch.float32, device=dev)
+    ws = _workspace(dev, L.mrg_colsum_workspace_bytes(M, N))
+    with torch.cuda.device(dev):
+        st = L.mrg_colsum(x2.data_ptr(), out.data_ptr(), M, N, 0, ws.data_ptr(), ws.numel(),
+                          torch.cuda.current_stream(dev).cuda_stream)
+    _cabi.check(st, "mrg_colsum")
+    return out
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -63,7 +79,7 @@ class _LinearFn(torch.autograd.Function):
             if M > 0:   # dW[N,K] = dyᵀ[N,M] · x[M,K]
                 _gemm(dy2, 1, N, x2, K, 1, None, dw, N, K, M, ctx.flags)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(dim=0)
+            db = _colsum(dy2)
         return dx, dw, db
 
 

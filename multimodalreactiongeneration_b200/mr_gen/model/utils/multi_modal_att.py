@@ -1,6 +1,10 @@
 """Mirror of mr_gen/model/utils/multi_modal_att.py — cross-modal nn.MultiheadAttention stack.
-Out of the CUDA hot path: plain torch, kept so SimpleLSTM is complete."""
+The projections around the attention run on the library's tcgen05 GEMM (``B200MultiheadAttention``,
+``B200Linear``); softmax(QK^T)V is torch's SDPA (fused attention is "next")."""
 from torch import nn
+
+from ....attention import B200MultiheadAttention
+from ....linear import B200Linear
 
 from .residual_connection import ResidualConnection
 
@@ -8,10 +12,10 @@ from .residual_connection import ResidualConnection
 class MultiModalAttentionBlockSequential(nn.Module):
     def __init__(self, modal1_feat_size=256, modal2_feat_size=256, num_head=1, dropout=0.0) -> None:
         super().__init__()
-        self.cross_modal_att = nn.MultiheadAttention(embed_dim=modal1_feat_size, num_heads=num_head,
+        self.cross_modal_att = B200MultiheadAttention(embed_dim=modal1_feat_size, num_heads=num_head,
                                                      dropout=dropout, batch_first=True,
                                                      kdim=modal2_feat_size, vdim=modal2_feat_size)
-        self.projection = nn.Linear(modal1_feat_size, modal1_feat_size)
+        self.projection = B200Linear(modal1_feat_size, modal1_feat_size)
 
     def forward(self, modal1, modal2):
         att, _ = self.cross_modal_att(query=modal1, key=modal2, value=modal2, need_weights=False)

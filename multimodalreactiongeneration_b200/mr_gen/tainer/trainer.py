@@ -19,31 +19,95 @@ import torch.distributed as dist
 from torch import nn
 
 
-class FlatGradBucket:
-    """All gradients of ``module`` in one contiguous fp32 buffer (the only collective of the path)."""
+_ALIGN = 64  # floats: every parameter starts on a 256-byte boundary (TMA needs 16-byte aligned weights)
 
-    def __init__(self, module: nn.Module):
+
+class FlatGradBucket:
+    """All gradients of ``module`` in one contiguous fp32 buffer (the only collective of the path).
+
+    On CUDA the PARAMETERS are re-homed into a second flat buffer with the same offsets, so that the optimizer
+    step can run as one streamed kernel over (param, grad, exp_avg, exp_avg_sq) — ``FlatAdamW``.  The
+    ``nn.Parameter`` objects, their names and shapes are untouched (``state_dict`` keys stay the reference's)."""
+
+    def __init__(self, module: nn.Module, flatten_params: bool = True):
         self.params = [p for p in module.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets = []
         off = 0
         for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_params = None
+        if flatten_params and dev.type == "cuda" and all(p.dtype == torch.float32 for p in self.params):
+            self.flat_params = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            p.grad = self.flat[o:o + n].view_as(p)
+            if self.flat_params is not None:
+                dst = self.flat_params[o:o + n].view_as(p)
+                dst.copy_(p.data)
+                p.data = dst
 
     def zero(self) -> None:
         self.flat.zero_()
 
-    def all_reduce_mean(self) -> None:
+    def all_reduce_sum(self) -> int:
+        """SUM over the ranks; returns the world size (the mean's 1/world is folded into the optimizer)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / dist.get_world_size())
+            return dist.get_world_size()
+        return 1
+
+    def all_reduce_mean(self) -> None:
+        world = self.all_reduce_sum()
+        if world > 1:
+            self.flat.mul_(1.0 / world)
 
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * 4
+
+
+class FlatAdamW:
+    """``torch.optim.AdamW`` arithmetic as ONE kernel over the flat buckets (C-ABI ``mrg_adamw_flat``).
+
+    Hyper-parameters are read from the torch optimizer that the model's ``configure_optimizers`` returned
+    (``param_groups[0]``) at every step, so LR schedulers that mutate it keep working; the step counter and the
+    bias corrections live on the device (CUDA-graph replay advances them)."""
+
+    def __init__(self, bucket: FlatGradBucket, optimizer: torch.optim.Optimizer):
+        from ... import _cabi
+        self._cabi = _cabi
+        self.bucket = bucket
+        self.optimizer = optimizer
+        n = bucket.flat.numel()
+        dev = bucket.flat.device
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.state = torch.zeros(3, dtype=torch.float32, device=dev)
+
+    @staticmethod
+    def applicable(bucket: FlatGradBucket, optimizer) -> bool:
+        if bucket.flat_params is None or type(optimizer) is not torch.optim.AdamW or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        same = len(g["params"]) == len(bucket.params) and all(a is b for a, b in zip(g["params"], bucket.params))
+        return same and not g.get("amsgrad", False) and not g.get("maximize", False)
+
+    def step(self, grad_scale: float = 1.0, zero_grad: bool = True) -> None:
+        g = self.optimizer.param_groups[0]
+        lr = g["lr"]
+        lr_dev = lr.data_ptr() if torch.is_tensor(lr) else None
+        b = self.bucket
+        dev = b.flat.device
+        with torch.cuda.device(dev):
+            st = self._cabi.lib().mrg_adamw_flat(
+                b.flat_params.data_ptr(), b.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                b.flat.numel(), lr_dev, 0.0 if lr_dev else float(lr), float(g["betas"][0]), float(g["betas"][1]),
+                float(g["eps"]), float(g["weight_decay"]), self.state.data_ptr(), float(grad_scale),
+                1 if zero_grad else 0, torch.cuda.current_stream(dev).cuda_stream)
+        self._cabi.check(st, "mrg_adamw_flat")
 
 
 def broadcast_parameters(module: nn.Module, src: int = 0) -> None:
@@ -79,14 +143,21 @@ class Trainer:
         # the bucket must own the .grad tensors before the optimizer is created
         self.bucket = FlatGradBucket(model)
         self.optimizer, self.scheduler = build_optimizer(model)
+        # AdamW on CUDA: one fused kernel over the flat buckets; anything else (SGD, CPU tests) steps through torch
+        self.flat_opt = FlatAdamW(self.bucket, self.optimizer) if FlatAdamW.applicable(self.bucket, self.optimizer) \
+            else None
         self.global_step = 0
 
     def train_step(self, batch) -> torch.Tensor:
-        self.bucket.zero()
+        if self.flat_opt is None:
+            self.bucket.zero()
         loss = self.model.training_step(batch)["loss"]
         loss.backward()
-        self.bucket.all_reduce_mean()
-        self.optimizer.step()
+        if self.flat_opt is not None:   # mean = SUM all-reduce, 1/world folded into the step; grads cleared by it
+            self.flat_opt.step(grad_scale=1.0 / self.bucket.all_reduce_sum(), zero_grad=True)
+        else:
+            self.bucket.all_reduce_mean()
+            self.optimizer.step()
         self.global_step += 1
         return loss.detach()
 

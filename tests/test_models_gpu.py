@@ -239,3 +239,96 @@ def test_streaming_generator_matches_free_running_prediction():
             got.append(gen.step(batch[0][0][:, t * ratio:(t + 1) * ratio], batch[1][0][:, t], prev).clone())
         got = torch.stack(got, dim=1)
         assert rel_err(got, want) <= 5e-5, graph
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """Trainer's fused optimizer step (mrg_adamw_flat over the flat buckets) vs torch.optim.AdamW, 5 steps,
+    including a learning-rate change between steps (what CosineAnnealingLR does to param_groups[0]["lr"])."""
+    import copy
+    from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import FlatAdamW, FlatGradBucket
+    torch.manual_seed(7)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 19), torch.nn.Tanh(), torch.nn.Linear(19, 5)).cuda()
+    ref = copy.deepcopy(net)
+    bucket = FlatGradBucket(net)
+    assert bucket.flat_params is not None and all(p.data_ptr() % 256 == 0 for p in net.parameters())
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-3, weight_decay=1e-2)
+    assert FlatAdamW.applicable(bucket, opt)
+    flat = FlatAdamW(bucket, opt)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=3e-3, weight_decay=1e-2)
+    for step in range(5):
+        x = torch.randn(11, 37, device="cuda")
+        if step == 3:
+            opt.param_groups[0]["lr"] = ropt.param_groups[0]["lr"] = 1e-3
+        net(x).square().sum().backward()
+        flat.step(grad_scale=0.5, zero_grad=True)       # grads were "summed over 2 ranks"
+        ropt.zero_grad()
+        (0.5 * ref(x).square().sum()).backward()
+        ropt.step()
+        assert float(bucket.flat.abs().max()) == 0.0     # cleared by the step
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert rel_err(a, b) <= 2e-6
+
+
+def test_trainer_uses_fused_optimizer_and_keeps_state_dict_keys():
+    from multimodalreactiongeneration_b200.mr_gen.configs import simple_lstm_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.simple_lstm.simple_lstm import SimpleLSTM
+    from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer
+    torch.manual_seed(0)
+    model = SimpleLSTM(*simple_lstm_cfg()).cuda()
+    keys = list(model.state_dict().keys())
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    tr = Trainer(model)
+    assert tr.flat_opt is not None
+    assert list(model.state_dict().keys()) == keys
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k])                 # re-homing the parameters does not change them
+    g = torch.Generator().manual_seed(3)
+    batch = (torch.randn(4, 20, 80, generator=g).cuda(), torch.randn(4, 20, 6, generator=g).cuda(),
+             torch.randn(4, 1, 6, generator=g).cuda())
+    tr.optimizer.param_groups[0]["lr"] = 1e-3
+    l0 = float(tr.train_step(batch))
+    for _ in range(20):
+        l1 = float(tr.train_step(batch))
+    assert l1 < l0
+
+
+@pytest.mark.parametrize("kdim,same_kv", [(None, True), (None, False), (96, True)])
+def test_b200_multihead_attention_matches_torch(kdim, same_kv):
+    """Projections on the tcgen05 GEMM, SDPA from torch: forward / input / parameter gradients vs nn.MultiheadAttention
+    (the reference's cross-modal call: batch_first, need_weights=False, key is value)."""
+    from multimodalreactiongeneration_b200 import B200MultiheadAttention
+    torch.manual_seed(11)
+    E, nh, B, Tq, Tk = 128, 2, 3, 37, 50
+    kw = dict(embed_dim=E, num_heads=nh, batch_first=True, kdim=kdim, vdim=kdim)
+    ref = torch.nn.MultiheadAttention(**kw).double()
+    mine = B200MultiheadAttention(**kw)
+    mine.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mine = mine.cuda()
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    q = torch.randn(B, Tq, E, dtype=torch.double)
+    k = torch.randn(B, Tk, kdim or E, dtype=torch.double)
+    v = k if same_kv else torch.randn(B, Tk, kdim or E, dtype=torch.double)
+    wq = torch.randn(B, Tq, E, dtype=torch.double)
+    qr, kr = q.clone().requires_grad_(True), k.clone().requires_grad_(True)
+    vr = kr if same_kv else v.clone().requires_grad_(True)
+    (ref(qr, kr, vr, need_weights=False)[0] * wq).sum().backward()
+    qm, km = q.float().cuda().requires_grad_(True), k.float().cuda().requires_grad_(True)
+    vm = km if same_kv else v.float().cuda().requires_grad_(True)
+    out, w = mine(qm, km, vm, need_weights=False)
+    assert w is None
+    (out * wq.float().cuda()).sum().backward()
+    with torch.no_grad():
+        want = ref(q, k, v, need_weights=False)[0]
+    assert rel_err(out.detach().cpu(), want) <= 2e-5
+    assert rel_l2(qm.grad.cpu(), qr.grad) <= 1e-4
+    assert rel_l2(km.grad.cpu(), kr.grad) <= 1e-4
+    for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        assert rel_l2(pm.grad.cpu(), pr.grad) <= 1e-4, name
+
+
+def test_colsum_matches_torch_sum():
+    from multimodalreactiongeneration_b200.linear import _colsum
+    torch.manual_seed(5)
+    for M, N in [(19200, 256), (300, 64), (1, 8), (1000, 1028)]:
+        x = torch.randn(M, N, device="cuda")
+        assert rel_err(_colsum(x), x.double().sum(0)) <= 1e-5
