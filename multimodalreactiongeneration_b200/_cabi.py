@@ -8,7 +8,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint8, c_uint6
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libmrg_b200.so")
 
-F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE, F_ZERO_STATE, F_TF32, F_REC_V1 = 1, 2, 4, 8, 16, 32, 64
+F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE, F_ZERO_STATE, F_TF32, F_REC_V1, F_GEMM_V1 = 1, 2, 4, 8, 16, 32, 64, 128
 
 EXPORTS = (
     "mrg_version", "mrg_last_error_string", "mrg_device_info", "mrg_lstm_workspace_bytes",

@@ -260,7 +260,10 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // operand X(r, k): element (r,k) at ptr[r*s_r + k*s_k]; K-major if s_k == 1, MN-major if s_r == 1
-static int make_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k, int rows, int K, int* mn_major) {
+// `plain_mn`: an MN-major operand that is read element-wise by converter threads (the TMEM-operand kernel) is
+// loaded without swizzle (box = 32 rows x 32 k, 4 boxes per tile).
+int make_tc_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k, int rows, int K, int* mn_major,
+                int plain_mn) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return MRG_E_UNSUPPORTED; }
   cuuint64_t dims[2], strides[1];
@@ -278,7 +281,8 @@ static int make_map(CUtensorMap* map, const float* ptr, long long s_r, long long
   }
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         *mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         *mn_major ? (plain_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                                   : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MRG_E_INVALID; }
   return 0;
@@ -299,7 +303,7 @@ bool gemm_tc_supported(const GemmArgs& g) {
   return operand_ok(g.a, g.a_sm, g.a_sk) && operand_ok(g.b, g.b_sn, g.b_sk) && get_encode_fn() != nullptr;
 }
 
-static int tc_splits(int M, int N, int K) {
+int tc_splits(int M, int N, int K) {
   const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN);
   const int kb = (K + TBK - 1) / TBK;
   if (tiles >= 120 || kb < 16) return 1;
@@ -321,8 +325,8 @@ int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStre
   }
   CUtensorMap ma, mb;
   TcParams p = {};
-  if (int e = make_map(&ma, g.a, g.a_sm, g.a_sk, g.M, g.K, &p.a_mn)) return e;
-  if (int e = make_map(&mb, g.b, g.b_sn, g.b_sk, g.N, g.K, &p.b_mn)) return e;
+  if (int e = make_tc_map(&ma, g.a, g.a_sm, g.a_sk, g.M, g.K, &p.a_mn, 0)) return e;
+  if (int e = make_tc_map(&mb, g.b, g.b_sn, g.b_sk, g.N, g.K, &p.b_mn, 0)) return e;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.kb_total = (g.K + TBK - 1) / TBK;
   const int splits = tc_splits(g.M, g.N, g.K);

@@ -38,6 +38,8 @@ def _default_flags() -> int:
     f = 0
     if os.environ.get("MRG_GENERIC_REC", "0") == "1":
         f |= _cabi.F_GENERIC_REC
+    if os.environ.get("MRG_GEMM_V1", "0") == "1":
+        f |= _cabi.F_GEMM_V1
     if os.environ.get("MRG_REC_V1", "0") == "1":
         f |= _cabi.F_REC_V1
     if os.environ.get("MRG_SIMT_GEMM", "0") == "1":
