@@ -246,7 +246,7 @@ def run_ours(args):
     per_frame = BYTES_BWD_PER_FRAME if dom == "rec_bwd" else BYTES_FWD_PER_FRAME
     avg_ms = dom_ms / max(1, dom_n)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture
         with open(tpath) as fh:
             t = json.load(fh).get(dom)
@@ -266,7 +266,7 @@ def run_ours(args):
         "e2e": {"value": frames * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": f"{dom}_cluster_kernel<256>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": f"{dom}2_kernel<256, 4>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": frames_per_launch * per_frame,
                      "note": "latency-bound recurrence: T dependent steps per launch; see latency_us_per_timestep"},
