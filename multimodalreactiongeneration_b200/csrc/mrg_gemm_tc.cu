@@ -307,7 +307,7 @@ int tc_splits(int M, int N, int K) {
   const int tiles = ((M + TBM - 1) / TBM) * ((N + TBN - 1) / TBN);
   const int kb = (K + TBK - 1) / TBK;
   if (tiles >= 120 || kb < 16) return 1;
-  int s = (148 + tiles - 1) / tiles;
+  int s = 148 / tiles;  // one wave: never more CTAs than SMs
   if (s > kb / 8) s = kb / 8;
   return s < 1 ? 1 : s;
 }

@@ -12,13 +12,17 @@
 //
 // Warp roles: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 idle | 4-7 A converter (TMEM lane
 // quarter = warp % 4) | 8-11 B converter (hi / lo tiles in shared memory) | all 12: epilogue.
+#include <cstdlib>
+
 #include "mrg_tc_common.cuh"
 
 namespace mrg {
 
-constexpr int S2 = 4;                                       // pipeline stages
 constexpr int STAGE2_BYTES = 3 * TILE_BYTES;                // A raw, B_hi, B_lo
-constexpr int SMEM2_BYTES = S2 * STAGE2_BYTES + 1024 + 256;
+// S2 = pipeline stages: 4 with one CTA per SM (long K), or 2 with TWO co-resident CTAs per SM (short K: one CTA's
+// prologue / epilogue overlaps the other's main loop; 2 x (128 accumulator + 2 x 64 operand) TMEM columns)
+template <int S2>
+constexpr int smem2_bytes() { return S2 * STAGE2_BYTES + 1024 + 256; }
 constexpr int TC2_THREADS = 384;
 constexpr int ACC_COLS = 128;
 
@@ -46,7 +50,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
-__global__ void __launch_bounds__(TC2_THREADS, 1)
+template <int S2>
+__global__ void __launch_bounds__(TC2_THREADS, S2 == 2 ? 2 : 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -74,7 +79,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     mbar_init_fence();
   }
   if (warp == 2) {  // all 512 columns: 128 accumulator + 4 stages x 64 operand columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    if (S2 == 2) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -273,7 +279,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (S2 == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -286,7 +293,8 @@ __global__ void tc_splitk_reduce_kernel(TcParams p, int splits);
 int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<4>()));
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2_bytes<2>()));
     attr_set = true;
   }
   CUtensorMap ma, mb;
@@ -312,7 +320,16 @@ int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStr
   dim3 grid((g.N + TBN - 1) / TBN, (g.M + TBM - 1) / TBM, zdim);
   ProfScope prof(PROF_GEMM, stream);
   count_launch(zdim > 1 ? 2 : 1);
-  gemm_tc2_kernel<<<grid, TC2_THREADS, SMEM2_BYTES, stream>>>(ma, mb, p);
+  static int force_stages = -1;
+  if (force_stages < 0) {
+    const char* e = getenv("MRG_GEMM_STAGES");
+    force_stages = e ? atoi(e) : 0;
+  }
+  // short K (<= 16 k-blocks per CTA) or more CTAs than SMs: two co-resident CTAs per SM with 2 stages each
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  const bool two = force_stages ? force_stages == 2 : (p.kb_per_split <= 16 || ctas > 148);
+  if (two) gemm_tc2_kernel<2><<<grid, TC2_THREADS, smem2_bytes<2>(), stream>>>(ma, mb, p);
+  else gemm_tc2_kernel<4><<<grid, TC2_THREADS, smem2_bytes<4>(), stream>>>(ma, mb, p);
   MRG_CUDA_CHECK(cudaGetLastError());
   if (zdim > 1) {
     const long long total = (long long)g.M * g.N;
