@@ -54,6 +54,8 @@ extern "C" {
 #define MRG_F_TF32        32   /* reduced-precision mode: the projection GEMMs run ONE tf32 tensor-core
                                   pass (10-bit mantissa, >= bf16 precision) instead of the 3-pass
                                   fp32-grade split; the recurrence itself stays fp32               */
+#define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that
+                                  accumulate straight into the trainer's flat gradient bucket            */
 #define MRG_F_GEMM_V1    128   /* use the first-generation tensor-core GEMM (both operands in shared memory)  */
 #define MRG_F_REC_V1      64   /* use the first-generation cluster kernels (kept for A/B measurements)  */
 #define MRG_F_ZERO_STATE  16   /* caller guarantees h0 = c0 = 0 (hx=None): with T == 1 the layer is a

@@ -181,7 +181,8 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   ws += align_up((size_t)D * B * 4 * H * sizeof(float), 256);
   if (T == 1) ws += align_up((size_t)D * 4 * H * H * sizeof(float), 256);
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
-  const int acc = (flags & MRG_F_ACCUMULATE) ? 1 : 0;
+  const int acc = (flags & (MRG_F_ACCUMULATE | MRG_F_ACC_WEIGHTS)) ? 1 : 0;  // weight matrices
+  const int acc_b = (flags & MRG_F_ACCUMULATE) ? 1 : 0;                      // bias
 
   RecBwdArgs r = {};
   r.gates = gates;
@@ -208,7 +209,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   for (int d = 0; d < D; ++d) {
     const float* dpre = gates + (size_t)d * T * B * 4 * H;
     if (g[d].db)
-      if ((e = colsum_deinterleave(db_part + (size_t)d * B * 4 * H, g[d].db, B, H, acc, stream))) return e;
+      if ((e = colsum_deinterleave(db_part + (size_t)d * B * 4 * H, g[d].db, B, H, acc_b, stream))) return e;
     if (g[d].dw_ih) {
       GemmArgs m = {};
       m.a = dpre; m.a_sm = 1; m.a_sk = 4 * H;

@@ -287,13 +287,23 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
     if (n + 3 < N) o[n + 3] = s.w;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int slabs, int N,
-                                    int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = accumulate ? out[n] : 0.f;
-  for (int i = 0; i < slabs; ++i) s += partial[(size_t)i * N + n];
-  out[n] = s;
+// pass 2: 32 columns x 8 slab lanes per block; lane l adds slabs l, l+8, ... then the 8 lanes are added in order
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                           int slabs, int N, int accumulate) {
+  __shared__ float red[8][32];
+  const int c = threadIdx.x & 31, l = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  float s = 0.f;
+  if (n < N)
+    for (int i = l; i < slabs; i += 8) s += partial[(size_t)i * N + n];
+  red[l][c] = s;
+  __syncthreads();
+  if (l == 0 && n < N) {
+    float t = accumulate ? out[n] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][c];
+    out[n] = t;
+  }
 }
 }  // namespace mrg
 
@@ -320,7 +330,7 @@ extern "C" int mrg_colsum(const float* x, float* out, int M, int N, int accumula
   MRG_REQUIRE(N % 4 == 0, "mrg_colsum: N must be a multiple of 4 (16-byte aligned rows)");
   mrg::colsum_slab_kernel<<<dim3((N + 255) / 256, slabs), 256, 0, stream>>>(x, (float*)workspace, M, N);
   MRG_CUDA_CHECK(cudaGetLastError());
-  mrg::colsum_final_kernel<<<(N + 255) / 256, 256, 0, stream>>>((const float*)workspace, out, slabs, N, accumulate);
+  mrg::colsum_final_kernel<<<(N + 31) / 32, 256, 0, stream>>>((const float*)workspace, out, slabs, N, accumulate);
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

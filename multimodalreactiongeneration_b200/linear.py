@@ -14,31 +14,45 @@ from . import _cabi
 from .lstm import _default_flags, _workspace
 
 
-def _gemm(a, a_sm, a_sk, b, b_sk, b_sn, bias, c, M, N, K, flags):
+def _gemm(a, a_sm, a_sk, b, b_sk, b_sn, bias, c, M, N, K, flags, accumulate=0):
     L = _cabi.lib()
     dev = c.device
     ws = _workspace(dev, L.mrg_gemm_workspace_bytes(M, N, K))
     with torch.cuda.device(dev):
         st = L.mrg_gemm_strided(a.data_ptr(), a_sm, a_sk, b.data_ptr(), b_sk, b_sn, _cabi.ptr(bias), c.data_ptr(),
-                                N, M, N, K, 0, 0, ws.data_ptr(), ws.numel(), flags,
+                                N, M, N, K, accumulate, 0, ws.data_ptr(), ws.numel(), flags,
                                 torch.cuda.current_stream(dev).cuda_stream)
     _cabi.check(st, "mrg_gemm_strided")
 
 
-def _colsum(x2):
-    """Column sums of a contiguous [M, N] fp32 matrix (bias gradient) through the C-ABI; torch only for N % 4 != 0."""
+def _colsum(x2, into=None):
+    """Column sums of a contiguous [M, N] fp32 matrix (bias gradient) through the C-ABI; torch only for N % 4 != 0.
+    ``into``: accumulate into this [N] tensor instead of returning a new one."""
     M, N = x2.shape
     if N % 4 != 0 or x2.data_ptr() % 16 != 0:
-        return x2.sum(dim=0)
+        s = x2.sum(dim=0)
+        if into is None:
+            return s
+        into.add_(s)
+        return None
     L = _cabi.lib()
     dev = x2.device
-    out = torch.empty(N, dtype=torch.float32, device=dev)
+    out = torch.empty(N, dtype=torch.float32, device=dev) if into is None else into
     ws = _workspace(dev, L.mrg_colsum_workspace_bytes(M, N))
     with torch.cuda.device(dev):
-        st = L.mrg_colsum(x2.data_ptr(), out.data_ptr(), M, N, 0, ws.data_ptr(), ws.numel(),
+        st = L.mrg_colsum(x2.data_ptr(), out.data_ptr(), M, N, 0 if into is None else 1, ws.data_ptr(), ws.numel(),
                           torch.cuda.current_stream(dev).cuda_stream)
     _cabi.check(st, "mrg_colsum")
-    return out
+    return out if into is None else None
+
+
+def fused_grad_target(p):
+    """The trainer's flat gradient bucket owns ``p.grad`` and is cleared by the optimizer kernel: weight-gradient
+    kernels may then ADD straight into it (and return no gradient to autograd) instead of writing a temporary that
+    autograd adds with one more launch per parameter."""
+    if getattr(p, "_mrg_grad_fused", False) and p.grad is not None and p.grad.is_contiguous():
+        return p.grad
+    return None
 
 
 class _LinearFn(torch.autograd.Function):
@@ -56,6 +70,7 @@ class _LinearFn(torch.autograd.Function):
         if M > 0:
             _gemm(x2, K, 1, weight.contiguous(), 1, K, bias, y, M, N, K, flags)
         ctx.save_for_backward(x2, weight)
+        ctx.params = (weight, bias)   # the python objects (saved_tensors may hand back fresh wrappers)
         ctx.has_bias = bias is not None
         ctx.flags = flags
         return y.view(*x.shape[:-1], N)
@@ -73,13 +88,20 @@ class _LinearFn(torch.autograd.Function):
             if M > 0:   # dx[M,K] = dy[M,N] · W[N,K]
                 _gemm(dy2, N, 1, w, K, 1, None, dx, M, K, N, ctx.flags)
             dx = dx.view(*dy.shape[:-1], K)
+        wp, bp = ctx.params
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros((N, K), dtype=torch.float32, device=dy.device) if M == 0 else \
-                torch.empty((N, K), dtype=torch.float32, device=dy.device)
-            if M > 0:   # dW[N,K] = dyᵀ[N,M] · x[M,K]
-                _gemm(dy2, 1, N, x2, K, 1, None, dw, N, K, M, ctx.flags)
+            tgt = fused_grad_target(wp)
+            if tgt is not None:   # accumulate into the flat bucket, nothing for autograd to add
+                if M > 0:
+                    _gemm(dy2, 1, N, x2, K, 1, None, tgt, N, K, M, ctx.flags, accumulate=1)
+            else:
+                dw = torch.zeros((N, K), dtype=torch.float32, device=dy.device) if M == 0 else \
+                    torch.empty((N, K), dtype=torch.float32, device=dy.device)
+                if M > 0:   # dW[N,K] = dyᵀ[N,M] · x[M,K]
+                    _gemm(dy2, 1, N, x2, K, 1, None, dw, N, K, M, ctx.flags)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _colsum(dy2)
+            tgt = fused_grad_target(bp)
+            db = _colsum(dy2, into=tgt)
         return dx, dw, db
 
 

@@ -150,6 +150,16 @@ class _LSTMLayerFn(torch.autograd.Function):
                                    None if dh0 is None else dh0[d].data_ptr(),
                                    None if dc0 is None else dc0[d].data_ptr())
             grads += [g_ih, g_hh, g_b if b_ih is not None else None, g_b if b_hh is not None else None]
+        # weight gradients straight into the trainer's flat bucket (linear.fused_grad_target) when every weight
+        # matrix of the layer allows it: one launch per parameter less, no temporaries
+        from .linear import fused_grad_target
+        tg = [fused_grad_target(weights[4 * d + i]) for d in range(D) for i in (0, 1)]
+        fused = all(t is not None for t in tg)
+        if fused:
+            for d in range(D):
+                dg[d].dw_ih, dg[d].dw_hh = tg[2 * d].data_ptr(), tg[2 * d + 1].data_ptr()
+                grads[4 * d], grads[4 * d + 1] = None, None
+            flags |= _cabi.F_ACC_WEIGHTS
         nbytes = L.mrg_lstm_workspace_bytes(T, B, I, H, D)
         ws = _workspace(dev, nbytes)
         stream = torch.cuda.current_stream(dev).cuda_stream

@@ -48,6 +48,8 @@ class FlatGradBucket:
                 dst = self.flat_params[o:o + n].view_as(p)
                 dst.copy_(p.data)
                 p.data = dst
+                # the optimizer kernel clears the bucket every step: weight-gradient kernels may add into it
+                p._mrg_grad_fused = os.environ.get("MRG_FUSED_WGRAD", "1") != "0"
 
     def zero(self) -> None:
         self.flat.zero_()
