@@ -54,6 +54,8 @@ extern "C" {
 #define MRG_F_TF32        32   /* reduced-precision mode: the projection GEMMs run ONE tf32 tensor-core
                                   pass (10-bit mantissa, >= bf16 precision) instead of the 3-pass
                                   fp32-grade split; the recurrence itself stays fp32               */
+#define MRG_F_CLUSTER_BUDGET(n) (((n) & 0xFF) << 16)  /* recurrent kernels use at most n clusters (0 = all): lets two
+                                  independent LSTM stacks (audio / motion encoders) run side by side on two streams */
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that
                                   accumulate straight into the trainer's flat gradient bucket            */
 #define MRG_F_GEMM_V1    128   /* use the first-generation tensor-core GEMM (both operands in shared memory)  */

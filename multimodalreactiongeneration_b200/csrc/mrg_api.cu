@@ -157,6 +157,7 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   r.T = T; r.B = B; r.H = H; r.D = D;
   r.train = (flags & MRG_F_TRAIN) ? 1 : 0;
   r.trace = debug_trace_buffer();
+  r.cluster_budget = (flags >> 16) & 0xFF;
   if (!(flags & (MRG_F_GENERIC_REC | MRG_F_REC_V1)) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
   if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) return rec_forward_cluster(r, stream);
   return rec_forward_generic(r, stream);
@@ -196,6 +197,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   }
   r.db_part = db_part;
   r.T = T; r.B = B; r.H = H; r.D = D;
+  r.cluster_budget = (flags >> 16) & 0xFF;
   int e;
   bool pointwise = (T == 1) && (flags & MRG_F_ZERO_STATE);
   for (int d = 0; d < D; ++d) pointwise = pointwise && !g[d].dh0 && !g[d].dc0;

@@ -256,6 +256,7 @@ struct RecArgs {
   int T, B, H, D;
   int train;
   unsigned long long* trace;  // developer event trace (-DMRG_REC_TRACE builds), else nullptr
+  int cluster_budget;         // > 0: use at most this many clusters (MRG_F_CLUSTER_BUDGET)
 };
 unsigned long long* debug_trace_buffer();
 int rec_forward_generic(const RecArgs& a, cudaStream_t stream);
@@ -274,6 +275,7 @@ struct RecBwdArgs {
   float* dc0[2];
   float* db_part;       // [D][B][H][4] per-row bias-gradient partials (sum over t)
   int T, B, H, D;
+  int cluster_budget;   // same meaning as in RecArgs
 };
 int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream);
@@ -284,7 +286,7 @@ int rec_backward_cluster2(const RecBwdArgs& a, cudaStream_t stream);
 bool rec2_supported(int H);
 int max_active_clusters2(int H);
 int rec2_max_chunks(int H, int rbc);
-void pick_partition2(int H, int B, int D, int* slices_out, int* nch_out, int* rbc_out);
+void pick_partition2(int H, int B, int D, int budget, int* slices_out, int* nch_out, int* rbc_out);
 
 int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
                             int has_state, cudaStream_t stream);

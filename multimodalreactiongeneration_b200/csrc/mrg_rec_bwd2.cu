@@ -386,7 +386,7 @@ int rec_backward_cluster2(const RecBwdArgs& a, cudaStream_t stream) {
   MRG_REQUIRE((long long)(a.T + 1) * a.B * a.H * 4 * a.D < (1LL << 31),
               "rec_backward_cluster2: T*B*4H*D exceeds the 32-bit index range");
   int slices, nch, rbc;
-  pick_partition2(a.H, a.B, a.D, &slices, &nch, &rbc);
+  pick_partition2(a.H, a.B, a.D, a.cluster_budget, &slices, &nch, &rbc);
   if (a.H == 256) return rbc == 2 ? launch_bwd2<256, 2>(a, slices, nch, stream) : launch_bwd2<256, 4>(a, slices, nch, stream);
   if (a.H == 128) return rbc == 2 ? launch_bwd2<128, 2>(a, slices, nch, stream) : launch_bwd2<128, 4>(a, slices, nch, stream);
   set_error("rec_backward_cluster2: unsupported hidden size %d", a.H);

@@ -375,9 +375,10 @@ bool rec2_supported(int H) { return H == 128 || H == 256; }
 // FFMA2 issue per row, so few large chunks win as soon as two of them cover each other's tail + DSMEM
 // flight: 4-row chunks, at least 2 of them; clusters with <= 3 rows run one row per chunk.
 // MRG_REC_NCH / MRG_REC_RBC override nch / rbc (tuning experiments).
-void pick_partition2(int H, int B, int D, int* slices_out, int* nch_out, int* rbc_out) {
+void pick_partition2(int H, int B, int D, int budget, int* slices_out, int* nch_out, int* rbc_out) {
   int maxc = max_active_clusters2(H);
   if (maxc <= 0) maxc = H == 256 ? 15 : 30;
+  if (budget > 0 && budget < maxc) maxc = budget;
   int per_dir = maxc / D;
   if (per_dir < 1) per_dir = 1;
   int slices = B < per_dir ? B : per_dir;
@@ -408,7 +409,7 @@ int rec_forward_cluster2(const RecArgs& a, cudaStream_t stream) {
   MRG_REQUIRE((long long)(a.T + 1) * a.B * a.H * 4 < (1LL << 31),
               "rec_forward_cluster2: T*B*4H exceeds the 32-bit index range of one direction");
   int slices, nch, rbc;
-  pick_partition2(a.H, a.B, a.D, &slices, &nch, &rbc);
+  pick_partition2(a.H, a.B, a.D, a.cluster_budget, &slices, &nch, &rbc);
   if (a.H == 256) return rbc == 2 ? launch_fwd2<256, 2>(a, slices, nch, stream) : launch_fwd2<256, 4>(a, slices, nch, stream);
   if (a.H == 128) return rbc == 2 ? launch_fwd2<128, 2>(a, slices, nch, stream) : launch_fwd2<128, 4>(a, slices, nch, stream);
   set_error("rec_forward_cluster2: unsupported hidden size %d", a.H);

@@ -46,10 +46,31 @@ def _default_flags() -> int:
         f |= _cabi.F_SIMT_GEMM
     if _PRECISION["mode"] == "tf32":
         f |= _cabi.F_TF32
+    f |= (_BUDGET["clusters"] & 0xFF) << 16
     return f
 
 
 _PRECISION = {"mode": os.environ.get("MRG_PRECISION", "fp32")}
+_BUDGET = {"clusters": 0}
+
+
+class cluster_budget:
+    """Context manager: the recurrent kernels launched inside use at most ``n`` thread-block clusters, so that two
+    independent LSTM stacks running on two CUDA streams (e.g. the audio and the motion encoder of SimpleLSTM) fit on the
+    GPU side by side instead of queueing behind each other.  The budget is stored with the autograd node, so the
+    BPTT kernels of those layers use it too."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+
+    def __enter__(self):
+        self.prev = _BUDGET["clusters"]
+        _BUDGET["clusters"] = self.n
+        return self
+
+    def __exit__(self, *exc):
+        _BUDGET["clusters"] = self.prev
+        return False
 
 
 def set_precision(mode: str) -> None:

@@ -4,6 +4,7 @@ MotionDecoder :100, SimpleLSTM :146) on the B200 LSTM path.
 Documented deviation: at the reference's HEAD the three sub-modules pass the
 ``(tensor, states)`` tuple returned by ``LSTMLayerd`` on as if it were a tensor and ``forward`` raises;
 here element ``[0]`` is taken, which is what the code did before its ``hx`` refactor."""
+import os
 from collections import OrderedDict
 from typing import Dict
 
@@ -95,10 +96,37 @@ class SimpleLSTM(LightningModule):
         self.delta_order = metrics.delta_order
 
     def forward(self, acoustic_feature: torch.Tensor, motion_feature: torch.Tensor) -> torch.Tensor:
-        audio = self.acoustic_encoder(acoustic_feature)
-        motion = self.motion_encoder(motion_feature)
+        if acoustic_feature.is_cuda and os.environ.get("MRG_TWO_STREAMS", "1") != "0":
+            audio, motion = self._encode_two_streams(acoustic_feature, motion_feature)
+        else:
+            audio = self.acoustic_encoder(acoustic_feature)
+            motion = self.motion_encoder(motion_feature)
         fused = self.multimodal_att(motion, audio)
         return self.motion_decoder(fused)
+
+    def _encode_two_streams(self, acoustic_feature, motion_feature):
+        """The two encoders are independent until the cross-modal attention: run them on two CUDA streams with
+        half of the co-resident clusters each.  A persistent recurrent kernel is latency-bound per timestep, so two of
+        them side by side (more rows per cluster, fewer clusters) finish sooner than one after the other, and the
+        projection GEMMs of one stack fill the SMs the other's recurrence leaves idle.  Autograd replays each
+        backward node on the stream of its forward, so the BPTT kernels overlap the same way."""
+        from ....lstm import cluster_budget
+        from .... import _cabi
+        main = torch.cuda.current_stream(acoustic_feature.device)
+        if getattr(self, "_side_stream", None) is None or self._side_stream.device != acoustic_feature.device:
+            self._side_stream = torch.cuda.Stream(device=acoustic_feature.device)
+            info = [__import__("ctypes").c_int() for _ in range(5)]
+            _cabi.lib().mrg_device_info(*[__import__("ctypes").byref(v) for v in info])
+            self._half_clusters = max(1, info[1].value // 2)
+        side = self._side_stream
+        side.wait_stream(main)
+        with cluster_budget(self._half_clusters):
+            with torch.cuda.stream(side):
+                motion = self.motion_encoder(motion_feature)
+            audio = self.acoustic_encoder(acoustic_feature)
+        main.wait_stream(side)
+        motion.record_stream(main)
+        return audio, motion
 
     def lossfun(self):
         return nn.MSELoss(reduction="mean")

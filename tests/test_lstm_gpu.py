@@ -291,3 +291,28 @@ def test_reduced_precision_tf32_mode_within_stated_bound():
     assert 1e-6 < err <= 2e-2
     for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
         assert rel_l2(pm.grad.cpu(), pr.grad) <= 5e-2, name
+
+
+@pytest.mark.parametrize("budget", [1, 7])
+def test_cluster_budget_gives_identical_results(budget):
+    """MRG_F_CLUSTER_BUDGET only changes how the batch rows are cut over clusters / chunks, never the arithmetic per
+    (row, unit): forward states and all gradients must be bit-identical to the unrestricted launch."""
+    from multimodalreactiongeneration_b200 import lstm_layer
+    from multimodalreactiongeneration_b200.lstm import cluster_budget
+    torch.manual_seed(9)
+    T, B, H = 25, 64, 256
+    x = torch.randn(T, B, H, device="cuda")
+    k = 1.0 / np.sqrt(H)
+    w = [torch.empty(4 * H, H, device="cuda").uniform_(-k, k), torch.empty(4 * H, H, device="cuda").uniform_(-k, k),
+         torch.empty(4 * H, device="cuda").uniform_(-k, k), torch.empty(4 * H, device="cuda").uniform_(-k, k)]
+    outs = []
+    for b in (0, budget):
+        ws = [t.clone().requires_grad_(True) for t in w]
+        xx = x.clone().requires_grad_(True)
+        with cluster_budget(b):
+            y, h, c = lstm_layer(xx, ws, H, 1)
+        (y.sin().sum() + c.sum()).backward()
+        outs.append((y, h, c, xx.grad, ws[1].grad, ws[2].grad))
+    for a, b_ in zip(*outs[:2]):
+        assert torch.equal(a, b_) or rel_err(a, b_) <= 1e-6
+    assert torch.equal(outs[0][0], outs[1][0])   # the forward is bit-identical
