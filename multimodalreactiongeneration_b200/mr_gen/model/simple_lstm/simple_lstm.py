@@ -76,6 +76,10 @@ class MotionDecoder(nn.Module):
 
 
 class SimpleLSTM(LightningModule):
+    # sub-modules whose backward completes first, in that order: the trainer all-reduces their gradient slice while
+    # the encoders' BPTT still runs (each is used once per forward)
+    ddp_overlap_children = ("motion_decoder", "multimodal_att")
+
     def __init__(self, cfg, optim, metrics):
         super().__init__()
         self.cfg, self.optim, self.metrics = cfg, optim, metrics

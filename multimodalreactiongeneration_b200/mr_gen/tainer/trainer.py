@@ -61,6 +61,17 @@ class FlatGradBucket:
             return dist.get_world_size()
         return 1
 
+    def child_range(self, module: nn.Module, child_name: str):
+        """[start, end) of the flat bucket that holds the gradients of ``module.<child_name>`` (parameters are laid
+        out in registration order, so a sub-module owns one contiguous range)."""
+        ids = {id(p) for p in getattr(module, child_name).parameters() if p.requires_grad}
+        idx = [i for i, p in enumerate(self.params) if id(p) in ids]
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            return None
+        last = idx[-1]
+        end = self.offsets[last + 1] if last + 1 < len(self.offsets) else self.flat.numel()
+        return self.offsets[idx[0]], end
+
     def all_reduce_mean(self) -> None:
         world = self.all_reduce_sum()
         if world > 1:
@@ -149,16 +160,66 @@ class Trainer:
         self.flat_opt = FlatAdamW(self.bucket, self.optimizer) if FlatAdamW.applicable(self.bucket, self.optimizer) \
             else None
         self.global_step = 0
+        # Bucketed, overlapped gradient all-reduce: a model may name the sub-modules whose backward finishes early
+        # (`ddp_overlap_children`, each used exactly ONCE per forward); their slice of the flat bucket is all-reduced
+        # asynchronously as soon as their backward is done, while the rest of the backward still runs.  Everything
+        # else goes out in one all-reduce after the backward, as before.
+        self._early = []          # [(start, end)] in firing order
+        self._early_done = []
+        self._handles = []
+        self._in_backward = False
+        self.n_early_all_reduces = 0   # early (overlapped) all-reduces issued so far
+        if _world() > 1 and os.environ.get("MRG_DDP_OVERLAP", "1") != "0":
+            for name in getattr(model, "ddp_overlap_children", ()):
+                rng = self.bucket.child_range(model, name)
+                if rng is None:
+                    continue
+                k = len(self._early)
+                self._early.append(rng)
+                self._early_done.append(False)
+                getattr(model, name).register_full_backward_hook(
+                    lambda m, gin, gout, k=k: self._child_backward_done(k, gin))
+
+    def _child_backward_done(self, k: int, grad_input) -> None:
+        # fires when the gradients w.r.t. the sub-module's INPUTS exist, i.e. after every node inside it has run
+        if not self._in_backward or self._early_done[k] or not any(g is not None for g in grad_input):
+            return
+        a, b = self._early[k]
+        self._handles.append(dist.all_reduce(self.bucket.flat[a:b], op=dist.ReduceOp.SUM, async_op=True))
+        self._early_done[k] = True
+        self.n_early_all_reduces += 1
+
+    def _all_reduce_rest(self) -> int:
+        """SUM all-reduce of whatever the early hooks did not cover; returns the world size."""
+        world = _world()
+        if world <= 1:
+            return 1
+        flat = self.bucket.flat
+        done = sorted(r for r, d in zip(self._early, self._early_done) if d)
+        pos = 0
+        for a, b in done + [(flat.numel(), flat.numel())]:
+            if a > pos:
+                self._handles.append(dist.all_reduce(flat[pos:a], op=dist.ReduceOp.SUM, async_op=True))
+            pos = max(pos, b)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        self._early_done = [False] * len(self._early)
+        return world
 
     def train_step(self, batch) -> torch.Tensor:
         if self.flat_opt is None:
             self.bucket.zero()
         loss = self.model.training_step(batch)["loss"]
+        self._in_backward = True
         loss.backward()
+        self._in_backward = False
+        world = self._all_reduce_rest()
         if self.flat_opt is not None:   # mean = SUM all-reduce, 1/world folded into the step; grads cleared by it
-            self.flat_opt.step(grad_scale=1.0 / self.bucket.all_reduce_sum(), zero_grad=True)
+            self.flat_opt.step(grad_scale=1.0 / world, zero_grad=True)
         else:
-            self.bucket.all_reduce_mean()
+            if world > 1:
+                self.bucket.flat.mul_(1.0 / world)
             self.optimizer.step()
         self.global_step += 1
         return loss.detach()
@@ -223,6 +284,10 @@ class Trainer:
             if self.ckpt_dir and _rank() == 0:
                 save_checkpoint(self.model, os.path.join(self.ckpt_dir, "last.ckpt"), epoch, self.global_step)
         return history
+
+
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 def _rank() -> int:

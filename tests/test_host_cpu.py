@@ -175,3 +175,74 @@ def test_flat_gradient_bucket_data_parallel_gloo_world2(tmp_path):
         capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DDP_OK" in out.stdout
+
+
+_WORKER_OVERLAP = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer, init_distributed
+
+
+class Toy(torch.nn.Module):
+    # `head` finishes its backward first, then `mid`; `stem` is left for the trailing all-reduce
+    ddp_overlap_children = ("head", "mid")
+
+    def __init__(self):
+        super().__init__()
+        self.stem = torch.nn.Linear(5, 7)
+        self.mid = torch.nn.Sequential(torch.nn.Tanh(), torch.nn.Linear(7, 6))
+        self.head = torch.nn.Linear(6, 3)
+
+    def forward(self, x):
+        return self.head(torch.tanh(self.mid(self.stem(x))))
+
+    def training_step(self, batch):
+        x, y = batch
+        return {"loss": torch.nn.functional.mse_loss(self(x), y)}
+
+    def configure_optimizers(self):
+        return {"optimizer": torch.optim.SGD(self.parameters(), lr=0.1)}
+
+
+world = init_distributed("gloo")
+rank = dist.get_rank()
+torch.manual_seed(100 + rank)
+net = Toy()
+tr = Trainer(net)                                   # broadcasts rank 0's weights, registers the early hooks
+assert len(tr._early) == 2, tr._early
+torch.manual_seed(7)
+x_all, y_all = torch.randn(8, 5), torch.randn(8, 3)
+shard = slice(rank * 4, rank * 4 + 4)
+for _ in range(3):
+    tr.train_step((x_all[shard], y_all[shard]))
+assert tr.n_early_all_reduces == 6, tr.n_early_all_reduces   # both early slices went out in every step
+flat = torch.cat([p.detach().flatten() for p in net.parameters()])
+gathered = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(gathered, flat)
+if rank == 0:
+    torch.manual_seed(100)
+    ref = Toy()
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for _ in range(3):
+        ropt.zero_grad()
+        ref.training_step((x_all, y_all))["loss"].backward()
+        ropt.step()
+    rflat = torch.cat([p.detach().flatten() for p in ref.parameters()])
+    assert torch.allclose(gathered[0], gathered[1]), "ranks diverged"
+    assert torch.allclose(gathered[0], rflat, atol=1e-6), float((gathered[0] - rflat).abs().max())
+    print("DDP_OVERLAP_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_trainer_overlapped_bucket_all_reduce_gloo_world2(tmp_path):
+    """Early (per sub-module) + trailing all-reduce of the flat bucket must give the single-process trajectory."""
+    script = tmp_path / "worker_overlap.py"
+    script.write_text(_WORKER_OVERLAP)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+         "127.0.0.1", "--master-port", "29533", str(script), ROOT],
+        capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "DDP_OVERLAP_OK" in out.stdout
