@@ -39,3 +39,25 @@ def lstm_with_sampling_cfg(hidden=256, layers=2, sampler_hidden=128, sampler_lay
                        momentum=0.9)
     metrics = DictConfig(use_centroid=True, use_angle=True, delta_order=0)
     return model, optim, metrics
+
+
+def metaformer_cfg(hidden=256, blocks=5, encoder_layers=5, bottleneck=64, heads=4, acoustic=80, ratio=1,
+                   scheduled=False, max_epochs=100, mixers=("lstm", "lstm", "lstm"), seed=None):
+    """lstmformer (``Metaformer``): the reference's mr_gen/model/lstmformer/config.yaml model block on the synthetic
+    shapes — modalities (audio, partner motion, own motion), own motion is the main stream."""
+    model = DictConfig(
+        main_modal_idx=2, hidden_size=hidden, dropout=0.0, num_block=blocks, num_layerd=1,
+        encoder_num_layer=encoder_layers, num_internal_layer=1, residual=True, residual_layer_norm=True, bias=True,
+        emb_mixers=list(mixers), bottleneck_size=bottleneck, nonlinearity="none", ffn_nonlinearity="relu",
+        proj_size=0, num_heads=heads, add_bias_kv=False, add_zero_attn=False, max_context_len=10,
+        repeat_with_encoder=False, interlayer_residual=False, interlayer_residual_norm=True,
+        sampling_rate=48000, shift=1600 // ratio, pred_fps=30.0,
+        modalities=["audio", "motion", "motion"], use_centroid=True, use_angle=True, nmels=acoustic - 1,
+        delta_order=0, loss_type="huber", loss_reduction="mean", huber_delta=1.0, smoothl1_beta=1.0,
+        delta_loss_scale=1, use_scheduled_sampling=scheduled, max_epochs=max_epochs)
+    if seed is not None:
+        model["sampling_seed"] = seed
+    optim = DictConfig(use_optimizer="adam", lr=5e-6, weight_decay=1e-2, use_lr_sched=True, max_epochs=100,
+                       momentum=0.9)
+    metrics = DictConfig(use_centroid=True, use_angle=True, delta_order=0)
+    return model, optim, metrics

@@ -70,10 +70,84 @@ def lws_batch(g, B=3, T=7, lead=2, ratio=2, A=10, P=6, pad_rows=1):
             (target, lens)]
 
 
+def metaformer_cfg(ns, scheduled=False):
+    """reference lstmformer/config.yaml model block at test size (hidden 32, 2 blocks, 2-layer encoders)"""
+    model = ns.AttrDict(
+        main_modal_idx=2, hidden_size=32, dropout=0.0, num_block=2, num_layerd=1, encoder_num_layer=2,
+        num_internal_layer=1, residual=True, residual_layer_norm=True, bias=True,
+        emb_mixers=["lstm", "lstm", "lstm"], bottleneck_size=8, nonlinearity="none", ffn_nonlinearity="relu",
+        proj_size=0, num_heads=4, add_bias_kv=False, add_zero_attn=False, max_context_len=10,
+        repeat_with_encoder=False, interlayer_residual=False, interlayer_residual_norm=True,
+        sampling_rate=16000, shift=160, pred_fps=50.0,  # ratio = 100/50 = 2
+        modalities=["audio", "motion", "motion"], use_centroid=True, use_angle=True, nmels=9, delta_order=0,
+        loss_type="huber", loss_reduction="mean", huber_delta=1.0, smoothl1_beta=1.0, delta_loss_scale=1,
+        use_scheduled_sampling=scheduled, max_epochs=6)
+    _, optim, metrics = lws_cfg(ns)
+    return model, optim, metrics
+
+
+def metaformer_fixture(ns):
+    """7. Metaformer (lstmformer): forward, teacher-forced step, attention masks, rollout in 3 modes, scheduled-
+    sampling training step — all from the unmodified reference on CPU."""
+    from mr_gen.model.lstmformer.lstmformer import Metaformer
+    from mr_gen.model.utils.multi_modal_metaformer import gen_attention_mask
+
+    torch.manual_seed(7)
+    m = Metaformer(*metaformer_cfg(ns))
+    g = torch.Generator().manual_seed(707)
+    batch = lws_batch(g)
+    names = ["acoustic", "motion_p", "motion_s", "lead_a", "lead_p", "lead_s", "target"]
+    ins = {n: batch[i][0].clone() for i, n in enumerate(names)}
+    y, hxs = m.forward(*batch[:-1])
+    leaves = []
+
+    def walk(o):
+        if isinstance(o, dict):
+            for v in o.values():
+                walk(v)
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                walk(v)
+        else:
+            leaves.append(o)
+    walk(hxs)
+    assert len(hxs) == 2 and all(leaf is None for leaf in leaves)   # Q3
+    outs = {"y": y}
+    own = torch.cat([batch[5][0], batch[2][0]], dim=1)
+    audio = torch.cat([batch[3][0], batch[0][0]], dim=1)
+    outs["mask_own_audio"] = gen_attention_mask(own, audio, 4)
+    outs["mask_own_own"] = gen_attention_mask(own, own, 4)
+    outs["mask_audio_own"] = gen_attention_mask(audio, own, 4)
+    tf_batch = [(t.clone(), l) for t, l in batch]
+    loss = m.training_step(tf_batch)["loss"]
+    loss.backward()
+    outs["loss"] = loss
+    grads = {k: p.grad.clone() for k, p in m.named_parameters()}
+    with torch.no_grad():
+        outs["pred_tf"], outs["target_tf"] = m.prediction([(t.clone(), l) for t, l in batch])
+        outs["pred_free"], _ = m.prediction([(t.clone(), l) for t, l in batch], full_generation=True)
+        m.current_epoch = 3
+        torch.manual_seed(77)
+        ins["mask_ss"] = torch.rand(batch[1][0].shape[1]) < (3 / 6)
+        torch.manual_seed(77)
+        outs["pred_ss"], _ = m.prediction([(t.clone(), l) for t, l in batch], use_scheduled_sampling=True)
+    m.zero_grad()
+    m.use_scheduled_sampling = True
+    torch.manual_seed(77)
+    loss_ss = m.training_step([(t.clone(), l) for t, l in batch])["loss"]
+    loss_ss.backward()
+    outs["loss_ss"] = loss_ss
+    grads.update({"ss/" + k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    _save("metaformer", m.state_dict(), ins, outs, grads, {"ratio": m.ratio, "lead_len": batch[4][0].shape[1]})
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     ns = load_reference()
+    if "--only-metaformer" in sys.argv:
+        return metaformer_fixture(ns)
 
     # ---- 1. LSTMLayerd as used by lstm_with_sampling (uni, residual+LN, no FFN) -----------
     torch.manual_seed(1)
@@ -186,6 +260,8 @@ def main():
         _save("lstm_mixer_layerd", m.state_dict(), {"x": x, "w": w}, {"y": y},
               {**{k: p.grad for k, p in m.named_parameters()}, "x": x.grad},
               {"hx_is_none": hx is None})
+
+    metaformer_fixture(ns)
 
 
 if __name__ == "__main__":

@@ -246,3 +246,34 @@ def test_trainer_overlapped_bucket_all_reduce_gloo_world2(tmp_path):
         capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DDP_OVERLAP_OK" in out.stdout
+
+
+def test_metaformer_mirror_keeps_reference_keys_masks_and_arguments():
+    """lstmformer mirror: checkpoint keys of the unmodified reference (golden fixture), the causal-rectangular
+    attention masks (index arithmetic here vs the reference's tile/transpose construction), argument selection."""
+    from multimodalreactiongeneration_b200.mr_gen.configs import metaformer_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstmformer.lstmformer import Metaformer
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.argparser import mixer_layerd_argments_select
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.mixer_block import MixerLayerdFactory
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.multi_modal_metaformer import gen_attention_mask
+    sd, ins, outs, _, _ = load_golden("metaformer")
+    m = Metaformer(*metaformer_cfg(hidden=32, blocks=2, encoder_layers=2, bottleneck=8, heads=4, acoustic=10,
+                                   ratio=2, max_epochs=6))
+    mine = m.state_dict()
+    assert list(mine.keys()) == list(sd.keys())
+    assert all(mine[k].shape == sd[k].shape for k in sd)
+    m.load_state_dict(sd)
+    own = torch.cat([ins["lead_s"], ins["motion_s"]], 1)
+    audio = torch.cat([ins["lead_a"], ins["acoustic"]], 1)
+    for q, k, name in ((own, audio, "mask_own_audio"), (own, own, "mask_own_own"), (audio, own, "mask_audio_own")):
+        got = gen_attention_mask(q, k, 4)
+        assert got.shape == outs[name].shape and torch.equal(got, outs[name].bool()), name
+    with pytest.raises(ValueError):
+        gen_attention_mask(torch.zeros(1, 3, 2), torch.zeros(1, 5, 2), 2)
+    lstm_kw = mixer_layerd_argments_select("lstm", hidden_size=8, num_heads=4, proj_size=0, kdim=8)
+    assert "num_heads" not in lstm_kw and "kdim" not in lstm_kw and lstm_kw["proj_size"] == 0
+    assert mixer_layerd_argments_select("conv", hidden_size=8) is None
+    with pytest.raises(NotImplementedError):   # GRU mixers: SURVEY §8(f) item 1, never a cuDNN fallback
+        MixerLayerdFactory().build("gru", mixer_layerd_argments_select("gru", hidden_size=8))
+    with pytest.raises(ValueError):
+        MixerLayerdFactory().build("conv", {})

@@ -355,3 +355,91 @@ def test_fused_weight_gradients_equal_autograd_accumulation(monkeypatch):
         flats.append(bucket.flat.clone())
     assert float(flats[0].abs().max()) > 0
     assert rel_l2(flats[0], flats[1]) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lstmformer (Metaformer): 3 LSTM-mixer stacks + masked cross-modal attention, fixture from the unmodified reference
+# ---------------------------------------------------------------------------------------------------------
+def _metaformer(scheduled=False, **kw):
+    from multimodalreactiongeneration_b200.mr_gen.configs import metaformer_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstmformer.lstmformer import Metaformer
+    return Metaformer(*metaformer_cfg(hidden=32, blocks=2, encoder_layers=2, bottleneck=8, heads=4, acoustic=10,
+                                      ratio=2, max_epochs=6, scheduled=scheduled, **kw))
+
+
+def _leaves(o):
+    if isinstance(o, dict):
+        o = list(o.values())
+    if isinstance(o, (list, tuple)):
+        return [leaf for v in o for leaf in _leaves(v)]
+    return [o]
+
+
+def test_metaformer_forward_and_teacher_forced_step():
+    sd, ins, outs, grads, meta = load_golden("metaformer")
+    m = _metaformer()
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    assert m.ratio == int(meta["ratio"])
+    y, hxs = m.forward(*_lws_batch(ins)[:-1])
+    assert len(hxs) == 2 and all(leaf is None for leaf in _leaves(hxs))   # Q3: no state comes back
+    assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
+    loss = m.training_step(_lws_batch(ins))["loss"]
+    loss.backward()
+    assert abs(float(loss) - float(outs["loss"])) <= 1e-4 * abs(float(outs["loss"]))
+    _check_grads(m, grads)
+
+
+@pytest.mark.parametrize("rollout", ["wavefront", "stepwise"])
+def test_metaformer_rollout_modes(rollout):
+    sd, ins, outs, _, _ = load_golden("metaformer")
+    m = _metaformer()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.rollout = rollout
+    with torch.no_grad():
+        tf, target = m.prediction(_lws_batch(ins))
+        free, _ = m.prediction(_lws_batch(ins), full_generation=True)
+        ss, _ = m.prediction(_lws_batch(ins), use_scheduled_sampling=True, sampling_mask=ins["mask_ss"].bool())
+    assert target.shape == outs["target_tf"].shape and torch.equal(target.cpu(), outs["target_tf"])  # [T,B,T,P] sic
+    assert rel_err(tf.cpu(), outs["pred_tf"]) <= OUT_TOL
+    assert rel_err(free.cpu(), outs["pred_free"]) <= 5e-5   # 7 free-running steps compound fp32 rounding
+    assert rel_err(ss.cpu(), outs["pred_ss"]) <= 5e-5
+
+
+def test_metaformer_scheduled_sampling_training_step():
+    sd, ins, outs, grads, _ = load_golden("metaformer")
+    m = _metaformer(scheduled=True)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.current_epoch = 3
+    torch.manual_seed(77)   # the fixture's draw: torch.rand(T) < 3/6
+    loss = m.training_step(_lws_batch(ins))["loss"]
+    loss.backward()
+    assert abs(float(loss) - float(outs["loss_ss"])) <= 1e-4 * abs(float(outs["loss_ss"]))
+    for name, p in m.named_parameters():
+        if "ss/" + name in grads:
+            assert rel_l2(p.grad.cpu(), grads["ss/" + name]) <= GRAD_TOL, name
+
+
+def test_metaformer_headline_shape_trains_through_the_trainer():
+    """cfg 4 shape at reduced batch (hidden 256, 5 blocks, 5-layer encoders = 15 LSTM mixers, T=300): one Trainer
+    step runs, the loss is finite and every parameter receives a gradient through the fused optimizer."""
+    from multimodalreactiongeneration_b200.mr_gen.configs import metaformer_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstmformer.lstmformer import Metaformer
+    from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer
+    torch.manual_seed(0)
+    m = Metaformer(*metaformer_cfg()).cuda()
+    tr = Trainer(m)
+    g = torch.Generator().manual_seed(1)
+    B, T, lead = 8, 300, 30
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    batch = [(r(B, T, 80), None), (r(B, T, 6), None), (r(B, T, 6), None), (r(B, lead, 80), None),
+             (r(B, lead, 6), None), (r(B, lead, 6), None), (r(B, T, 6), None)]
+    before = tr.bucket.flat_params.clone()
+    loss = tr.train_step(batch)
+    assert torch.isfinite(loss)
+    moved = (tr.bucket.flat_params != before)
+    for p, o in zip(tr.bucket.params, tr.bucket.offsets):
+        assert bool(moved[o:o + p.numel()].any())
