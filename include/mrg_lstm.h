@@ -157,6 +157,24 @@ int mrg_adamw_flat(float* p, float* g, float* m, float* v, size_t n, const float
                    float beta2, float eps, float weight_decay, float* state, float grad_scale, int zero_grad,
                    void* stream);
 
+/* Fused fp32 multi-head attention between the LSTM stacks.  Replaces the
+ * nn.MultiheadAttention core called at mr_gen/model/utils/multi_modal_att.py:12-31 (no mask) and at
+ * mr_gen/model/utils/for_sequential.py:25-50 with the mask of mr_gen/model/utils/multi_modal_metaformer.py:32-79.
+ * q [B,Tq,*], k / v [B,Tk,*], o [B,Tq,*]: head h occupies columns h*hd .. h*hd+hd-1 of a row, ld* = row stride in
+ * floats (batch stride = T*ld; k and v may be the halves of one fused projection output).  hd in {32, 64}; pointers
+ * 16-byte aligned, strides multiples of 4.  o = softmax(scale * q k^T + mask) v per (batch, head).
+ * mask_mode 0: none | 1: key j visible to query i iff j / rate <= i | 2: iff j <= i / rate; additionally (i, j) is
+ * masked when pad_q[b*Tq+i] and pad_k[b*Tk+j] are both non-zero (both NULL = no padding).  A query with no visible
+ * key yields 0 (torch: NaN).  lse [B,nh,Tq] (log2 domain) is saved for the backward; dvec [B,nh,Tq] is scratch. */
+int mrg_attention_forward(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
+                          int ldo, float* lse, int B, int nh, int Tq, int Tk, int hd, float scale, int mask_mode,
+                          int rate, const uint8_t* pad_q, const uint8_t* pad_k, void* stream);
+int mrg_attention_backward(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const float* o,
+                           int ldo, const float* lse, const float* dout, int lddo, float* dq, int lddq, float* dk,
+                           int lddk, float* dv, int lddv, float* dvec, int B, int nh, int Tq, int Tk, int hd,
+                           float scale, int mask_mode, int rate, const uint8_t* pad_q, const uint8_t* pad_k,
+                           void* stream);
+
 /* Developer hook: device buffer of 16*1024*2 uint64 that -DMRG_REC_TRACE builds of the recurrent kernels fill
  * with (clock, event) records; NULL disables.  No effect in regular builds. */
 int mrg_debug_set_trace(unsigned long long* buf);

@@ -28,7 +28,7 @@ from ...utils.metrics import MultiTargetMetrics, gen_target_dict
 from ..lstm_with_sampling.lstm_with_sample import philox_sampling_mask
 from ..simple_lstm.simple_lstm import _configure_optimizers
 from ..utils.argparser import feedforward_block_argments, mixer_layerd_argments_select
-from ..utils.multi_modal_metaformer import MultiModalMetaformer, gen_attention_mask
+from ..utils.multi_modal_metaformer import MultiModalMetaformer, gen_attention_mask, gen_attention_mask_spec
 from ..utils.values import PADDING_VALUE
 
 InputTypes = Tuple[torch.Tensor, torch.Tensor]
@@ -136,7 +136,10 @@ class Metaformer(LightningModule):
         own = torch.cat([leading_motion_self[0].to(dev), motion_self[0].to(dev)], dim=1)
 
         def mask(q, k):
-            return self._flat_mask(gen_attention_mask(q, k, self.num_heads, PADDING_VALUE))
+            if q.is_cuda:   # the rule itself: the fused attention kernel evaluates it, no mask tensor exists
+                return gen_attention_mask_spec(q, k, PADDING_VALUE)
+            m = gen_attention_mask(q, k, self.num_heads, PADDING_VALUE)
+            return m.reshape(-1, m.shape[2], m.shape[3])   # nn.MultiheadAttention's form, as the reference (:269-294)
 
         kinds = [self.main_mixer_type] + self.other_mixer_type
         self_masks = [mask(s, s) if kind == "mha" else None for kind, s in zip(kinds, (own, audio, partner))]
@@ -144,12 +147,6 @@ class Metaformer(LightningModule):
             own, [audio, partner], hxs, (None, None, self_masks[0]),
             [(None, None, self_masks[1]), (None, None, self_masks[2])], [mask(own, audio), mask(own, partner)])
         return y, hxs
-
-    @staticmethod
-    def _flat_mask(m: torch.Tensor) -> torch.Tensor:
-        """CUDA: keep the broadcast [B, heads, L, S] view (B200MultiheadAttention takes it as is).  Elsewhere:
-        nn.MultiheadAttention's [B*heads, L, S] form, as the reference builds it (:269-294)."""
-        return m if m.is_cuda else m.reshape(-1, m.shape[2], m.shape[3])
 
     # ------------------------------------------------------------------------------------------
     def lossfun(self):

@@ -13,12 +13,14 @@ the per-block ``{"emb": [...], "crm": [...]}`` dicts that ``forward`` returns on
 
 Difference in representation only: ``gen_attention_mask`` returns the ``[B, heads, L, S]`` mask as a broadcast
 VIEW of a ``[B, 1, L, S]`` tensor computed by index arithmetic (the reference materialises the tiled triangle and
-``repeat``s it per head: 92 MB of bools per mask at B=256, 4 heads, T=300)."""
+``repeat``s it per head: 92 MB of bools per mask at B=256, 4 heads, T=300), and on CUDA ``Metaformer`` does not
+build the tensor at all: ``gen_attention_mask_spec`` hands the fused attention kernel the rule itself."""
 from typing import Any, List, Optional, Tuple, Union
 
 import torch
 from torch import nn
 
+from ....attention import AttentionMaskSpec
 from ....linear import B200Linear
 from .mixer_block import FeedForward, MixerLayerdFactory, split_state
 from .residual_connection import ResidualConnection
@@ -36,27 +38,27 @@ def check_form_modal_num(modal_num: int, sameone, msg: str = None) -> list:
     return sameone
 
 
+def gen_attention_mask_spec(main_modal: torch.Tensor, other_modal: torch.Tensor,
+                            padding_value: float = PADDING_VALUE) -> AttentionMaskSpec:
+    """The reference's mask as a RULE (mode, rate, per-frame padding bytes) for the fused attention kernel, which
+    evaluates it on the fly and skips key tiles that are masked for a whole query tile."""
+    L, S = main_modal.shape[1], other_modal.shape[1]
+    if S % L != 0 and L % S != 0:
+        raise ValueError(f"other_modal_len must be divisible by main_modal_len. "
+                         f"main_modal_len: {L}, other_modal_len: {S}")
+    mode, rate = (1, S // L) if S % L == 0 else (2, L // S)
+    pad_q = (main_modal[:, :, 0] == padding_value).to(torch.uint8).contiguous()
+    pad_k = (other_modal[:, :, 0] == padding_value).to(torch.uint8).contiguous()
+    return AttentionMaskSpec(mode, rate, pad_q, pad_k)
+
+
 def gen_attention_mask(main_modal: torch.Tensor, other_modal: torch.Tensor, head_num: int,
                        padding_value: float = PADDING_VALUE) -> torch.Tensor:
     """bool ``[B, head_num, L, S]``, True = may NOT attend.  Causal between two streams whose frame rates differ
     by an integer factor: with ``S = r*L`` query frame i sees the keys of frames ``<= i`` (``j // r <= i``); with
     ``L = r*S`` query i sees keys ``j <= i // r``.  A (query, key) pair that is padding on BOTH sides (first
     feature == ``padding_value``) is masked as well."""
-    L, S = main_modal.shape[1], other_modal.shape[1]
-    if S % L != 0 and L % S != 0:
-        raise ValueError(f"other_modal_len must be divisible by main_modal_len. "
-                         f"main_modal_len: {L}, other_modal_len: {S}")
-    dev = main_modal.device
-    q = torch.arange(L, device=dev).view(L, 1)
-    k = torch.arange(S, device=dev).view(1, S)
-    if S % L == 0:
-        causal = torch.div(k, S // L, rounding_mode="floor") > q
-    else:
-        causal = k > torch.div(q, L // S, rounding_mode="floor")
-    pad_q = (main_modal[:, :, 0] == padding_value).unsqueeze(-1)      # [B, L, 1]
-    pad_k = (other_modal[:, :, 0] == padding_value).unsqueeze(1)      # [B, 1, S]
-    merged = (causal.unsqueeze(0) | (pad_q & pad_k)).unsqueeze(1)     # [B, 1, L, S]
-    return merged.expand(main_modal.shape[0], head_num, L, S)
+    return gen_attention_mask_spec(main_modal, other_modal, padding_value).materialize(head_num)
 
 
 class MultiModalEmbedding(nn.Module):
