@@ -18,6 +18,7 @@
 //    faster), mode 2 = iff j <= i / rate (queries run faster), plus "both sides padded" from two per-frame byte
 //    vectors; key tiles that are masked for a whole query tile are skipped.
 #include <cstddef>
+#include <cstdlib>
 
 #include "mrg_common.cuh"
 
@@ -26,20 +27,6 @@ namespace mrg {
 constexpr int AT_T = 64;         // queries / keys per tile
 constexpr int AT_LD = 68;        // row stride (floats) of the k-major [.][64] shared-memory tiles
 constexpr int AT_THREADS = 256;  // 16 x 16 threads, 4 x 4 scores each
-
-struct AttnArgs {
-  const float *q, *k, *v;
-  float* o;
-  float* lse;  // [B, heads, Tq]: m + log2(sum), log2 domain
-  const float* dout;
-  float* dvec;  // [B, heads, Tq]: dO . O
-  float *dq, *dk, *dv;
-  int B, nh, Tq, Tk;
-  int ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;  // row strides in floats; batch stride = T * ld
-  float scale, scale_log2;
-  int mask_mode, rate;
-  const unsigned char *pad_q, *pad_k;  // [B, Tq], [B, Tk] or both null
-};
 
 // dst[d][r] (k-major, for "sum over d") = src[(r0 + r) * ld + d]; rows past nrows are zero
 template <int HD>
@@ -63,6 +50,42 @@ __device__ __forceinline__ void load_tile_n(float* dst, const float* __restrict_
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + r < nrows) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld + c * 4));
     *reinterpret_cast<float4*>(dst + r * HD + c * 4) = v;
+  }
+}
+
+// A 64 x HD tile held in registers between its global load and its shared-memory store, so that the load of tile
+// t+1 is in flight while tile t is being multiplied (the transposed store cannot be done by cp.async).
+template <int HD>
+struct TileRegs {
+  float4 v[HD / 16];
+};
+template <int HD>
+__device__ __forceinline__ void tile_fetch(TileRegs<HD>& t, const float* __restrict__ src, int ld, int r0, int nrows) {
+  constexpr int C4 = HD / 4;
+#pragma unroll
+  for (int n = 0; n < HD / 16; ++n) {
+    const int f = threadIdx.x + n * AT_THREADS, r = f / C4, c = f % C4;
+    t.v[n] = r0 + r < nrows ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(r0 + r) * ld + c * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int HD>
+__device__ __forceinline__ void tile_put_t(float* dst, const TileRegs<HD>& t) {  // dst[d][r], stride AT_LD
+  constexpr int C4 = HD / 4;
+#pragma unroll
+  for (int n = 0; n < HD / 16; ++n) {
+    const int f = threadIdx.x + n * AT_THREADS, r = f / C4, c = f % C4;
+    float* p = dst + (c * 4) * AT_LD + r;
+    p[0] = t.v[n].x; p[AT_LD] = t.v[n].y; p[2 * AT_LD] = t.v[n].z; p[3 * AT_LD] = t.v[n].w;
+  }
+}
+template <int HD>
+__device__ __forceinline__ void tile_put_n(float* dst, const TileRegs<HD>& t) {  // dst[r][d], stride HD
+  constexpr int C4 = HD / 4;
+#pragma unroll
+  for (int n = 0; n < HD / 16; ++n) {
+    const int f = threadIdx.x + n * AT_THREADS, r = f / C4, c = f % C4;
+    *reinterpret_cast<float4*>(dst + r * HD + c * 4) = t.v[n];
   }
 }
 
@@ -144,7 +167,7 @@ __device__ __forceinline__ void at_scores(float (&s)[4][4], const float* Qt, con
 // forward
 // ---------------------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(AT_THREADS, HD == 32 ? 3 : 2) attn_fwd_kernel(AttnArgs a) {
   constexpr int NC = HD / 16;
   extern __shared__ __align__(16) float at_sm[];
   float* Qt = at_sm;                  // [HD][AT_LD]
@@ -169,11 +192,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(AttnArgs a) {
     for (int c = 0; c < NC; ++c) acc[i][c] = 0.f;
   }
   const int njt = at_key_tiles(a, min(i0 + AT_T, a.Tq) - 1);
+  TileRegs<HD> kr, vr;
+  tile_fetch<HD>(kr, kb, a.ldk, 0, a.Tk);
+  tile_fetch<HD>(vr, vb, a.ldv, 0, a.Tk);
   for (int jt = 0; jt < njt; ++jt) {
     const int j0 = jt * AT_T;
     __syncthreads();  // the previous tile's Kt / Vs / Pt have been consumed (also orders the Qt fill)
-    load_tile_t<HD>(Kt, kb, a.ldk, j0, a.Tk);
-    load_tile_n<HD>(Vs, vb, a.ldv, j0, a.Tk);
+    tile_put_t<HD>(Kt, kr);
+    tile_put_n<HD>(Vs, vr);
+    if (jt + 1 < njt) {  // next tile's global loads fly during this tile's arithmetic
+      tile_fetch<HD>(kr, kb, a.ldk, j0 + AT_T, a.Tk);
+      tile_fetch<HD>(vr, vb, a.ldv, j0 + AT_T, a.Tk);
+    }
     __syncthreads();
     float s[4][4];
     at_scores<HD>(s, Qt, Kt, a, mc, b, i0, j0, ty, tx);
@@ -220,7 +250,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(AttnArgs a) {
 // backward 1: dQ (and D = dO . O), query tile resident
 // ---------------------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(AT_THREADS, HD == 32 ? 3 : 2) attn_bwd_dq_kernel(AttnArgs a) {
   constexpr int NC = HD / 16;
   extern __shared__ __align__(16) float at_sm[];
   float* Qt = at_sm;                   // [HD][AT_LD]
@@ -261,12 +291,19 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(AttnArgs a) {
     for (int c = 0; c < NC; ++c) acc[i][c] = 0.f;
   }
   const int njt = at_key_tiles(a, min(i0 + AT_T, a.Tq) - 1);
+  TileRegs<HD> kr, vr;
+  tile_fetch<HD>(kr, kb, a.ldk, 0, a.Tk);
+  tile_fetch<HD>(vr, vb, a.ldv, 0, a.Tk);
   for (int jt = 0; jt < njt; ++jt) {
     const int j0 = jt * AT_T;
     __syncthreads();
-    load_tile_t<HD>(Kt, kb, a.ldk, j0, a.Tk);
-    load_tile_t<HD>(Vt, vb, a.ldv, j0, a.Tk);
-    load_tile_n<HD>(Ks, kb, a.ldk, j0, a.Tk);
+    tile_put_t<HD>(Kt, kr);
+    tile_put_n<HD>(Ks, kr);
+    tile_put_t<HD>(Vt, vr);
+    if (jt + 1 < njt) {
+      tile_fetch<HD>(kr, kb, a.ldk, j0 + AT_T, a.Tk);
+      tile_fetch<HD>(vr, vb, a.ldv, j0 + AT_T, a.Tk);
+    }
     __syncthreads();
     float s[4][4], dp[4][4];
     at_scores<HD>(s, Qt, Kt, a, mc, b, i0, j0, ty, tx);
@@ -303,7 +340,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(AttnArgs a) {
 // backward 2: dK, dV, key tile resident
 // ---------------------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(AT_THREADS, HD == 32 ? 3 : 2) attn_bwd_dkv_kernel(AttnArgs a) {
   constexpr int NC = HD / 16;
   extern __shared__ __align__(16) float at_sm[];
   float* Kt = at_sm;                   // [HD][AT_LD]
@@ -330,14 +367,21 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(AttnArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int c = 0; c < NC; ++c) dk[i][c] = dv[i][c] = 0.f;
-  const int nit = (a.Tq + AT_T - 1) / AT_T;
-  for (int it = at_first_query_tile(a, j0); it < nit; ++it) {
+  const int nit = (a.Tq + AT_T - 1) / AT_T, it0 = at_first_query_tile(a, j0);
+  TileRegs<HD> qr, dr;
+  tile_fetch<HD>(qr, qb, a.ldq, it0 * AT_T, a.Tq);
+  tile_fetch<HD>(dr, dob, a.lddo, it0 * AT_T, a.Tq);
+  for (int it = it0; it < nit; ++it) {
     const int i0 = it * AT_T;
     __syncthreads();
-    load_tile_t<HD>(Qt, qb, a.ldq, i0, a.Tq);
-    load_tile_t<HD>(dOt, dob, a.lddo, i0, a.Tq);
-    load_tile_n<HD>(Qs, qb, a.ldq, i0, a.Tq);
-    load_tile_n<HD>(dOs, dob, a.lddo, i0, a.Tq);
+    tile_put_t<HD>(Qt, qr);
+    tile_put_n<HD>(Qs, qr);
+    tile_put_t<HD>(dOt, dr);
+    tile_put_n<HD>(dOs, dr);
+    if (it + 1 < nit) {
+      tile_fetch<HD>(qr, qb, a.ldq, i0 + AT_T, a.Tq);
+      tile_fetch<HD>(dr, dob, a.lddo, i0 + AT_T, a.Tq);
+    }
     __syncthreads();
     float s[4][4], dp[4][4];
     at_scores<HD>(s, Qt, Kt, a, mc, b, i0, j0, ty, tx);
@@ -423,6 +467,18 @@ static int attn_check(const char* who, const AttnArgs& a, int hd) {
   MRG_REQUIRE((a.pad_q == nullptr) == (a.pad_k == nullptr), "%s: pad_q and pad_k go together", who);
   return 0;
 }
+// The CUDA-core kernels of this file are the default: measured on B200 (profiles/r1d_attention.txt) the warp-level
+// 3xTF32 tensor-core variant (mrg_attention_tc.cu, MRG_ATTENTION_TC=1) is SLOWER — legacy mma.sync tf32 throughput
+// plus the per-fragment hi/lo splitting cost more than the FMA work they replace at d = 32 / 64.
+static int attn_dispatch(const AttnArgs& a, int hd, int backward, cudaStream_t stream) {
+  static int tc = -1;
+  if (tc < 0) {
+    const char* e = getenv("MRG_ATTENTION_TC");
+    tc = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (tc) return attn_tc_launch(a, hd, backward, stream);
+  return hd == 32 ? attn_launch<32>(a, backward, stream) : attn_launch<64>(a, backward, stream);
+}
 #define AT_ALIGNED(p, ld) ((p) != nullptr && (((uintptr_t)(p)) & 15) == 0 && (ld) % 4 == 0 && (ld) >= nh * hd)
 
 }  // namespace mrg
@@ -440,7 +496,7 @@ extern "C" int mrg_attention_forward(const float* q, int ldq, const float* k, in
   if (int e = mrg::attn_check("mrg_attention_forward", a, hd)) return e;
   MRG_REQUIRE(AT_ALIGNED(q, ldq) && AT_ALIGNED(k, ldk) && AT_ALIGNED(v, ldv) && AT_ALIGNED(o, ldo),
               "mrg_attention_forward: q/k/v/o must be 16-byte aligned with row strides that are multiples of 4");
-  return hd == 32 ? mrg::attn_launch<32>(a, 0, (cudaStream_t)stream) : mrg::attn_launch<64>(a, 0, (cudaStream_t)stream);
+  return mrg::attn_dispatch(a, hd, 0, (cudaStream_t)stream);
 }
 
 extern "C" int mrg_attention_backward(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
@@ -460,5 +516,5 @@ extern "C" int mrg_attention_backward(const float* q, int ldq, const float* k, i
   MRG_REQUIRE(AT_ALIGNED(q, ldq) && AT_ALIGNED(k, ldk) && AT_ALIGNED(v, ldv) && AT_ALIGNED(o, ldo) &&
                   AT_ALIGNED(dout, lddo) && AT_ALIGNED(dq, lddq) && AT_ALIGNED(dk, lddk) && AT_ALIGNED(dv, lddv),
               "mrg_attention_backward: tensors must be 16-byte aligned with row strides that are multiples of 4");
-  return hd == 32 ? mrg::attn_launch<32>(a, 1, (cudaStream_t)stream) : mrg::attn_launch<64>(a, 1, (cudaStream_t)stream);
+  return mrg::attn_dispatch(a, hd, 1, (cudaStream_t)stream);
 }

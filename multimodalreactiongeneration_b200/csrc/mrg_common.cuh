@@ -295,6 +295,22 @@ int cell_zero_state_backward(float* gates, const float* c_ext, const float* dy, 
 
 int colsum_deinterleave(const float* part, float* db, int B, int H, int accumulate,
                         cudaStream_t stream);
+// fused attention (mrg_attention.cu: CUDA-core kernels, mrg_attention_tc.cu: tensor-core kernels)
+struct AttnArgs {
+  const float *q, *k, *v;
+  float* o;
+  float* lse;   // [B, heads, Tq]: m + log2(sum), log2 domain
+  const float* dout;
+  float* dvec;  // [B, heads, Tq]: dO . O
+  float *dq, *dk, *dv;
+  int B, nh, Tq, Tk;
+  int ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;  // row strides in floats; batch stride = T * ld
+  float scale, scale_log2;
+  int mask_mode, rate;
+  const unsigned char *pad_q, *pad_k;  // [B, Tq], [B, Tk] or both null
+};
+int attn_tc_launch(const AttnArgs& a, int hd, int backward, cudaStream_t stream);
+
 int max_active_clusters(int H);
 
 // launch accounting / live kernel timing (bench.py's gpu_launches and roofline numbers)
