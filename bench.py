@@ -250,6 +250,8 @@ def run_ours(args):
     iso = _cabi.profile_read()
     _cabi.profile_enable(False)
 
+    if graphed:
+        trainer.release_cuda_graph()   # before the process group goes away (see Trainer.release_cuda_graph)
     if rank != 0:
         return
     frames = world * B_PER_GPU * T_FRAMES
@@ -329,9 +331,28 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    _leave()
+
+
+def _leave():
+    """Multi-rank exit that cannot hang: every rank drains its device, meets the others at a barrier (so no peer is
+    still inside a collective) and then leaves WITHOUT the NCCL communicator teardown — at 8 ranks
+    ``destroy_process_group`` after CUDA-graph-captured collectives blocked for minutes after the result line had
+    been printed.  Single-process runs return normally."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        dist.destroy_process_group()
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    finally:
+        os._exit(0)
 
 
 if __name__ == "__main__":

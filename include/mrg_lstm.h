@@ -59,6 +59,8 @@ extern "C" {
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that
                                   accumulate straight into the trainer's flat gradient bucket            */
 #define MRG_F_GEMM_V1    128   /* use the first-generation tensor-core GEMM (both operands in shared memory)  */
+#define MRG_F_GEMM_V3    512   /* force the persistent (third-generation) GEMM; MRG_F_GEMM_V2 1024 forces the second  */
+#define MRG_F_GEMM_V2   1024
 #define MRG_F_REC_V1      64   /* use the first-generation cluster kernels (kept for A/B measurements)  */
 #define MRG_F_ZERO_STATE  16   /* caller guarantees h0 = c0 = 0 (hx=None): with T == 1 the layer is a
                                   pointwise cell on the projection (no recurrence, W_hh inert) — the

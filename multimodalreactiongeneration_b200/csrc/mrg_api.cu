@@ -8,6 +8,7 @@
 namespace mrg {
 int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int gemm_tc3(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 bool gemm_tc_supported(const GemmArgs& g);
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 
@@ -17,8 +18,17 @@ static int run_gemm(const GemmArgs& g_in, void* ws, size_t ws_bytes, int flags, 
   GemmArgs g = g_in;
   g.single_pass = (flags & MRG_F_TF32) ? 1 : 0;
 #ifdef MRG_HAVE_TC_GEMM
-  if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g))
-    return (flags & MRG_F_GEMM_V1) ? gemm_tc(g, ws, ws_bytes, stream) : gemm_tc2(g, ws, ws_bytes, stream);
+  if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) {
+    if (flags & MRG_F_GEMM_V1) return gemm_tc(g, ws, ws_bytes, stream);
+    static int v3 = -1;  // MRG_GEMM_V3: 1 = persistent kernel for every shape, 0 = never, unset = per-shape choice
+    if (v3 < 0) {
+      const char* e = getenv("MRG_GEMM_V3");
+      v3 = e ? (e[0] == '1' ? 1 : 0) : 2;
+    }
+    if (flags & MRG_F_GEMM_V2) return gemm_tc2(g, ws, ws_bytes, stream);
+    if (v3 == 1 || (flags & MRG_F_GEMM_V3)) return gemm_tc3(g, ws, ws_bytes, stream);
+    return gemm_tc2(g, ws, ws_bytes, stream);
+  }
 #endif
   return gemm_simt(g, ws, ws_bytes, stream);
 }

@@ -252,6 +252,14 @@ class Trainer:
             self._static_loss = self.train_step(self._static_batch)
         self.global_step -= 1  # the capture pass did not execute
 
+    def release_cuda_graph(self) -> None:
+        """Drop the captured step.  NCCL keeps a reference on every communicator a live CUDA graph has captured
+        collectives of, and tearing the process group down with such a graph alive can block (seen at 8 ranks)."""
+        torch.cuda.synchronize()
+        self._graph = None
+        self._static_loss = None
+        self._static_batch = None
+
     def train_step_graphed(self, batch) -> torch.Tensor:
         for dst, src in zip(self._static_batch, batch):
             dst.copy_(src, non_blocking=True)

@@ -23,7 +23,7 @@ for name, M, N, K, a_mn, b_mn in shapes:
     a_sm, a_sk = (1, M) if a_mn else (K, 1)
     b_sk, b_sn = (N, 1) if b_mn else (1, K)
     ws = torch.empty(L.mrg_gemm_workspace_bytes(M, N, K), dtype=torch.uint8, device="cuda")
-    for flags, tag in ((0, "tc2 "), (_cabi.F_TF32, "tc2 single-pass tf32"), (_cabi.F_GEMM_V1, "tc1 ")):
+    for flags, tag in ((_cabi.F_GEMM_V3, "tc3 "), (_cabi.F_GEMM_V2, "tc2 "), (_cabi.F_GEMM_V3 | _cabi.F_TF32, "tc3 single-pass tf32")):
         def run():
             st = L.mrg_gemm_strided(a.data_ptr(), a_sm, a_sk, b.data_ptr(), b_sk, b_sn, None, c.data_ptr(), N, M, N, K,
                                     0, 0, ws.data_ptr(), ws.numel(), flags, torch.cuda.current_stream().cuda_stream)
