@@ -18,7 +18,7 @@ EXPORTS = (
     "mrg_launch_count", "mrg_profile_enable", "mrg_profile_read", "mrg_gemm_strided",
     "mrg_gemm_workspace_bytes", "mrg_layernorm_workspace_bytes", "mrg_residual_layernorm_forward",
     "mrg_residual_layernorm_backward", "mrg_adamw_flat", "mrg_debug_set_trace", "mrg_colsum", "mrg_colsum_workspace_bytes",
-    "mrg_attention_forward", "mrg_attention_backward",
+    "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
 )
 
 
@@ -101,6 +101,11 @@ def lib() -> ctypes.CDLL:
                                          c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p]
     L.mrg_attention_backward.restype = c_int
+    L.mrg_gru_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.mrg_gru_forward.restype = c_int
+    L.mrg_gru_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                   c_int, c_int, c_void_p]
+    L.mrg_gru_backward.restype = c_int
     L.mrg_launch_count.restype = ctypes.c_ulonglong
     L.mrg_profile_enable.argtypes = [c_int]
     L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]

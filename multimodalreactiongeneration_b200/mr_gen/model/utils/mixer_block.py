@@ -8,14 +8,15 @@ The mixers lstmformer puts around them are mirrored as well so that ``Metaformer
 ``MLPMixer*`` :114-166,308-352,605-676 (plain Linear stacks), ``MHAforSequentail`` (for_sequential.py:8-50),
 ``MHAMixer`` :255-305, ``MHAMixerBlock`` :508-602, ``MHAMixerLayerd`` :845-963 (cross-modal integrators; their
 projections run on the tcgen05 GEMM through ``B200MultiheadAttention``), and the two factories :966-1017.
-The GRU mixers (:169-208, 355-428, 679-759) are SURVEY §8(f) item 1 — "next", not built: the factory raises
-``NotImplementedError`` for ``"gru"`` rather than falling back to cuDNN."""
+``GRUMixer`` :169-208, ``GRUMixerBlock`` :355-428, ``GRUMixerLayerd`` :679-759 run on
+``B200GRU`` (csrc/mrg_gru.cu) — never cuDNN."""
 from collections import OrderedDict
 from typing import Any, List, Optional, Tuple, Union
 
 import torch
 from torch import nn
 
+from ....gru import B200GRU
 from ....lstm import B200LSTM
 from ....linear import B200Linear
 from ....attention import B200MultiheadAttention
@@ -374,14 +375,93 @@ class MHAMixerLayerd(nn.Module):
         return (query, hx, (key, value, attn_mask))  # hx: remaining INPUT states (Q3)
 
 
-class _GRUNotBuilt:
-    def __init__(self, **kwargs):
-        raise NotImplementedError("GRU mixers are SURVEY.md §8(f) item 1 (next): no sm_100a GRU kernel yet and this "
-                                  "package never falls back to cuDNN")
+# ------------------------------------------------------------------------------------------------------
+# GRU mixer (emb_mixers: "gru", mr_gen/model/lstmformer/config_gru.yaml)
+# ------------------------------------------------------------------------------------------------------
+class GRUMixer(nn.Module):
+    def __init__(self, input_size: int, hidden_size: int, num_layers: int = 1, batch_first: bool = True,
+                 dropout: float = 0.0, bidirectional: bool = False, bias: bool = True, device: torch.device = None,
+                 dtype: torch.dtype = None):
+        super().__init__()
+        if num_layers < 1:
+            raise ValueError("num_layers must be greater than 0.")
+        if bidirectional:
+            if hidden_size % 2 != 0:
+                raise ValueError("hidden_size must be even number when bidirectional is True.")
+            hidden_size //= 2
+        self.mixer = B200GRU(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers,
+                             batch_first=batch_first, dropout=dropout, bidirectional=bidirectional, bias=bias,
+                             device=DEVICE if device is None else device, dtype=dtype)
+
+    def forward(self, x: torch.Tensor, hn: Optional[torch.Tensor]):
+        return self.mixer(x, hn)
+
+
+class GRUMixerBlock(nn.Module):
+    """ResidualConnection(GRUMixer) + FeedForward.  Like the reference (:412-415) a supplied state list is sliced
+    with ``hx[:1]`` — a one-element LIST, which ``nn.GRU`` / ``B200GRU`` reject; under Q3 no state is ever supplied."""
+
+    def __init__(self, hidden_size: int, num_layers: int = 1, dropout: float = 0.0, batch_first: bool = True,
+                 bidirectional: bool = False, nonlinearity=None, residual: bool = False,
+                 residual_layer_norm: bool = False, bottleneck_size: int = None, bias: bool = True,
+                 device: torch.device = None, dtype: torch.dtype = None):
+        super().__init__()
+        kw = {"bias": bias, "device": device, "dtype": dtype}
+        core = GRUMixer(input_size=hidden_size, hidden_size=hidden_size, num_layers=num_layers,
+                        batch_first=batch_first, dropout=dropout, bidirectional=bidirectional, **kw)
+        self.mixer = ResidualConnection(core, residual_layer_norm, hidden_size) if residual else core
+        if residual and residual_layer_norm and device is not None:
+            self.mixer.layer_norm.to(device)
+        self.feed_forward = FeedForward(hidden_size=hidden_size, bottleneck_size=bottleneck_size,
+                                        nonlinearity=nonlinearity, residual=residual,
+                                        residual_layer_norm=residual_layer_norm, **kw)
+
+    def forward(self, x, hx=None, prev_hx=None):
+        if isinstance(x, tuple):
+            x, hx, prev_hx = x
+        elif not isinstance(x, torch.Tensor):
+            raise TypeError(f"x must be torch.Tensor or tuple or list, but got {type(x)}.")
+        state, hx = (None, None) if hx is None else (hx[:1], hx[1:])
+        state = None if state == [] else state
+        hx = None if hx == [] else hx
+        prev_hx = [] if prev_hx is None else prev_hx
+        y, state = self.mixer(x, state)
+        y = self.feed_forward(y)
+        prev_hx.append(state)
+        return (y, hx, prev_hx)
+
+
+class GRUMixerLayerd(nn.Module):
+    def __init__(self, hidden_size: int, input_projection: bool = False, input_projection_size: int = None,
+                 output_projection: bool = False, output_projection_size: int = None, num_layerd: int = 1,
+                 num_internal_layer: int = 1, dropout: float = 0.0, batch_first: bool = True,
+                 bidirectional: bool = False, nonlinearity=None, residual: bool = False,
+                 residual_layer_norm: bool = False, bottleneck_size: int = None, bias: bool = True,
+                 device: torch.device = None, dtype: torch.dtype = None):
+        super().__init__()
+        kw = {"bias": bias, "device": device, "dtype": dtype}
+        self.input_projection, self.output_projection = _projections(
+            hidden_size, input_projection, input_projection_size, output_projection, output_projection_size, kw)
+        self.mixer = nn.ModuleList(
+            GRUMixerBlock(hidden_size=hidden_size, num_layers=num_internal_layer, dropout=dropout,
+                          batch_first=batch_first, bidirectional=bidirectional, nonlinearity=nonlinearity,
+                          residual=residual, residual_layer_norm=residual_layer_norm,
+                          bottleneck_size=bottleneck_size, **kw)
+            for _ in range(num_layerd))
+
+    def forward(self, x: torch.Tensor, hx=None, other=(None,)):
+        if self.input_projection is not None:
+            x = self.input_projection(x)
+        collected = None
+        for block in self.mixer:
+            x, hx, collected = block(x, hx, collected)
+        if self.output_projection is not None:
+            x = self.output_projection(x)
+        return (x, hx, other)  # hx = what is left of the INPUT list (Q3)
 
 
 class MixerBlockFactory:
-    _kinds = {"mlp": MLPMixerBlock, "gru": _GRUNotBuilt, "lstm": LSTMMixerBlock, "mha": MHAMixerBlock}
+    _kinds = {"mlp": MLPMixerBlock, "gru": GRUMixerBlock, "lstm": LSTMMixerBlock, "mha": MHAMixerBlock}
 
     def build(self, mixer_type: str, configs: dict):
         if mixer_type not in self._kinds:
@@ -390,7 +470,7 @@ class MixerBlockFactory:
 
 
 class MixerLayerdFactory:
-    _kinds = {"mlp": MLPMixerLayerd, "gru": _GRUNotBuilt, "lstm": LSTMMixerLayerd, "mha": MHAMixerLayerd}
+    _kinds = {"mlp": MLPMixerLayerd, "gru": GRUMixerLayerd, "lstm": LSTMMixerLayerd, "mha": MHAMixerLayerd}
 
     def build(self, mixer_type: str, configs: dict):
         if mixer_type not in self._kinds:

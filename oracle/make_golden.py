@@ -141,6 +141,20 @@ def metaformer_fixture(ns):
     _save("metaformer", m.state_dict(), ins, outs, grads, {"ratio": m.ratio, "lead_len": batch[4][0].shape[1]})
 
 
+def gru_mixer_fixture(ns):
+    """8. GRUMixerLayerd (lstmformer with emb_mixers: gru) from the unmodified reference."""
+    from mr_gen.model.utils.mixer_block import GRUMixerLayerd
+    torch.manual_seed(8)
+    m = GRUMixerLayerd(hidden_size=32, num_layerd=2, residual=True, residual_layer_norm=True, nonlinearity="none",
+                       device=torch.device("cpu"))
+    x = torch.randn(3, 7, 32, requires_grad=True)
+    y, hx, _ = m(x)
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    _save("gru_mixer_layerd", m.state_dict(), {"x": x, "w": w}, {"y": y},
+          {**{k: p.grad for k, p in m.named_parameters()}, "x": x.grad}, {"hx_is_none": hx is None})
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
@@ -148,6 +162,8 @@ def main():
     ns = load_reference()
     if "--only-metaformer" in sys.argv:
         return metaformer_fixture(ns)
+    if "--only-gru" in sys.argv:
+        return gru_mixer_fixture(ns)
 
     # ---- 1. LSTMLayerd as used by lstm_with_sampling (uni, residual+LN, no FFN) -----------
     torch.manual_seed(1)
@@ -262,6 +278,7 @@ def main():
               {"hx_is_none": hx is None})
 
     metaformer_fixture(ns)
+    gru_mixer_fixture(ns)
 
 
 if __name__ == "__main__":

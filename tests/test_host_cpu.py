@@ -273,7 +273,10 @@ def test_metaformer_mirror_keeps_reference_keys_masks_and_arguments():
     lstm_kw = mixer_layerd_argments_select("lstm", hidden_size=8, num_heads=4, proj_size=0, kdim=8)
     assert "num_heads" not in lstm_kw and "kdim" not in lstm_kw and lstm_kw["proj_size"] == 0
     assert mixer_layerd_argments_select("conv", hidden_size=8) is None
-    with pytest.raises(NotImplementedError):   # GRU mixers: SURVEY §8(f) item 1, never a cuDNN fallback
-        MixerLayerdFactory().build("gru", mixer_layerd_argments_select("gru", hidden_size=8))
+    gru = MixerLayerdFactory().build("gru", mixer_layerd_argments_select("gru", hidden_size=8, num_layerd=2,
+                                                                        residual=True, residual_layer_norm=True))
+    assert type(gru.mixer[0].mixer.module.mixer).__name__ == "B200GRU"   # never nn.GRU / cuDNN
+    with pytest.raises(RuntimeError):
+        gru(torch.zeros(1, 2, 8))                                         # and no CPU path
     with pytest.raises(ValueError):
         MixerLayerdFactory().build("conv", {})

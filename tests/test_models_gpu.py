@@ -443,3 +443,81 @@ def test_metaformer_headline_shape_trains_through_the_trainer():
     moved = (tr.bucket.flat_params != before)
     for p, o in zip(tr.bucket.params, tr.bucket.offsets):
         assert bool(moved[o:o + p.numel()].any())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GRU mixer (lstmformer with emb_mixers: gru): B200GRU against torch.nn.GRU fp64, the mixer stack against the reference
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("I,H,L,bi,B,T,with_hx", [
+    (256, 256, 1, False, 64, 20, False),   # lstmformer mixer shape
+    (32, 32, 2, False, 3, 9, True),        # two layers, carried state, ragged row group
+    (20, 16, 1, True, 5, 7, True),         # bidirectional
+    (256, 256, 1, False, 1, 1, True),      # a single frame (autoregressive step)
+    (64, 48, 1, False, 130, 5, False),
+])
+def test_gru_matches_torch_gru(I, H, L, bi, B, T, with_hx):
+    from multimodalreactiongeneration_b200 import B200GRU
+    torch.manual_seed(9)
+    ref = torch.nn.GRU(I, H, L, batch_first=True, bidirectional=bi).double()
+    mine = B200GRU(I, H, L, batch_first=True, bidirectional=bi)
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    mine.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mine = mine.cuda()
+    D = 2 if bi else 1
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, T, I, generator=g, dtype=torch.double)
+    h0 = torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5 if with_hx else None
+    wy = torch.randn(B, T, D * H, generator=g, dtype=torch.double)
+    wh = torch.randn(L * D, B, H, generator=g, dtype=torch.double)
+    xr = x.clone().requires_grad_(True)
+    hr = None if h0 is None else h0.clone().requires_grad_(True)
+    yr, hnr = ref(xr, hr)
+    ((yr * wy).sum() + (hnr * wh).sum()).backward()
+    xm = x.float().cuda().requires_grad_(True)
+    hm = None if h0 is None else h0.float().cuda().requires_grad_(True)
+    ym, hnm = mine(xm, hm)
+    ((ym * wy.float().cuda()).sum() + (hnm * wh.float().cuda()).sum()).backward()
+    assert rel_err(ym.cpu(), yr) <= OUT_TOL and rel_err(hnm.cpu(), hnr) <= OUT_TOL
+    assert rel_l2(xm.grad.cpu(), xr.grad) <= GRAD_TOL
+    for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        assert rel_l2(pm.grad.cpu(), pr.grad) <= GRAD_TOL, name
+    if h0 is not None:
+        assert rel_l2(hm.grad.cpu(), hr.grad) <= GRAD_TOL
+
+
+def test_gru_mixer_layerd_matches_reference():
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.mixer_block import GRUMixerLayerd
+    sd, ins, outs, grads, meta = load_golden("gru_mixer_layerd")
+    m = GRUMixerLayerd(hidden_size=32, num_layerd=2, residual=True, residual_layer_norm=True, nonlinearity="none",
+                       device=torch.device("cpu"))
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x = ins["x"].cuda().requires_grad_(True)
+    y, hx, _ = m(x)
+    assert hx is None and bool(meta["hx_is_none"])
+    (y * ins["w"].cuda()).sum().backward()
+    assert rel_err(y.cpu(), outs["y"]) <= OUT_TOL
+    assert rel_l2(x.grad.cpu(), grads["x"]) <= GRAD_TOL
+    _check_grads(m, grads)
+
+
+def test_metaformer_with_gru_mixers_runs_a_training_step():
+    """config_gru.yaml's mixer choice: every embedding stack on B200GRU, one Trainer step, all parameters move."""
+    from multimodalreactiongeneration_b200.mr_gen.configs import metaformer_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstmformer.lstmformer import Metaformer
+    from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer
+    torch.manual_seed(0)
+    m = Metaformer(*metaformer_cfg(hidden=64, blocks=2, encoder_layers=2, bottleneck=16, heads=2,
+                                   mixers=("gru", "gru", "gru"))).cuda()
+    tr = Trainer(m)
+    g = torch.Generator().manual_seed(1)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    B, T, lead = 4, 12, 3
+    batch = [(r(B, T, 80), None), (r(B, T, 6), None), (r(B, T, 6), None), (r(B, lead, 80), None),
+             (r(B, lead, 6), None), (r(B, lead, 6), None), (r(B, T, 6), None)]
+    before = tr.bucket.flat_params.clone()
+    assert torch.isfinite(tr.train_step(batch))
+    moved = tr.bucket.flat_params != before
+    for p, o in zip(tr.bucket.params, tr.bucket.offsets):
+        assert bool(moved[o:o + p.numel()].any())

@@ -150,3 +150,24 @@ def test_port_simple_lstm_matches_reference():
     loss.backward()
     for k, v in sdg.items():
         assert rel_err(v.grad, grads[k]) < 2e-5, k
+
+
+def test_numpy_gru_matches_torch_forward_and_autograd():
+    """oracle/gru_numpy.py pinned to torch.nn.GRU (fp64, CPU): outputs and every gradient."""
+    from oracle import gru_numpy
+    torch.manual_seed(11)
+    T, B, I, H = 6, 3, 5, 7
+    m = torch.nn.GRU(I, H, 1).double()
+    x = torch.randn(T, B, I, dtype=torch.double, requires_grad=True)
+    h0 = torch.randn(1, B, H, dtype=torch.double, requires_grad=True)
+    y, hn = m(x, h0)
+    wy = torch.randn_like(y)
+    (y * wy).sum().backward()
+    n = lambda t: t.detach().numpy()
+    yn, cache = gru_numpy.gru_layer_forward(n(x), n(m.weight_ih_l0), n(m.weight_hh_l0), n(m.bias_ih_l0),
+                                            n(m.bias_hh_l0), n(h0[0]))
+    assert np.abs(yn - n(y)).max() < 1e-12 and np.abs(yn[-1] - n(hn[0])).max() < 1e-12
+    grads = gru_numpy.gru_layer_backward(n(wy), n(x), cache, n(m.weight_ih_l0), n(m.weight_hh_l0))
+    for got, ref in zip(grads, (x.grad, m.weight_ih_l0.grad, m.weight_hh_l0.grad, m.bias_ih_l0.grad,
+                                m.bias_hh_l0.grad, h0.grad[0])):
+        assert np.abs(got - n(ref)).max() < 1e-10
