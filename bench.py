@@ -267,7 +267,7 @@ def run_ours(args):
     # six launches per direction share the GPU with the other encoder's kernel on a second stream
     avg_ms = iso[dom][0] / max(1, iso[dom][1])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1d_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one ncu --set full capture
         with open(tpath) as fh:
             t = json.load(fh).get(dom)
