@@ -178,13 +178,14 @@ int mrg_attention_backward(const float* q, int ldq, const float* k, int ldk, con
                            void* stream);
 
 /* GRU recurrence of lstmformer's GRU mixer (nn.GRU at mr_gen/model/utils/mixer_block.py:194).
- * gx [T][B][3H] = x W_ih^T + b_ih (gate order r, z, n; from the projection GEMM), w_hh [3H][H], b_hh [3H] or NULL,
+ * gx [T][B][3H] = x W_ih^T + b_ih (gate order r, z, n; from the projection GEMM), w_hh [3H][H], w_hh_t [H][3H] = its
+ * transpose or NULL (when given and H % 4 == 0 the forward streams columns: no cross-lane reduction), b_hh [3H] or NULL,
  * y_ext [T+1][B][H]: slot 0 = h0 on entry, slot t+1 = h_t on return; reserve [T][B][4][H] (r, z, n, W_hn h + b_hn),
  * written when train != 0.  Backward: dy [T][B][H] or NULL, dh_n [B][H] or NULL -> dgx / dgh [T][B][3H] (gradients of
  * the pre-activations seen from the input side (r, z, n) and from the hidden side (r, z, hn)), dh0 [B][H] or NULL;
  * dX = dgx W_ih, dW_ih = dgx^T X, dW_hh = dgh^T y_ext[0:T], db_ih / db_hh = column sums are the caller's GEMMs. */
-int mrg_gru_forward(const float* gx, const float* w_hh, const float* b_hh, float* y_ext, float* reserve, int T, int B,
-                    int H, int train, void* stream);
+int mrg_gru_forward(const float* gx, const float* w_hh, const float* w_hh_t, const float* b_hh, float* y_ext,
+                    float* reserve, int T, int B, int H, int train, void* stream);
 int mrg_gru_backward(const float* dy, const float* dh_n, const float* reserve, const float* y_ext, const float* w_hh,
                      float* dgx, float* dgh, float* dh0, int T, int B, int H, void* stream);
 

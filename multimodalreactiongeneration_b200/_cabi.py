@@ -101,7 +101,8 @@ def lib() -> ctypes.CDLL:
                                          c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
                                          c_void_p]
     L.mrg_attention_backward.restype = c_int
-    L.mrg_gru_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.mrg_gru_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p]
     L.mrg_gru_forward.restype = c_int
     L.mrg_gru_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_void_p]

@@ -39,8 +39,9 @@ class _GRULayerFn(torch.autograd.Function):
         train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward; this is the reliable signal
         reserve = torch.empty((T, B, 4, H), dtype=torch.float32, device=dev) if train else None
         whh = w_hh.contiguous()
+        whh_t = whh.t().contiguous() if H % 4 == 0 else None   # [H, 3H]: the forward kernel streams its columns
         with torch.cuda.device(dev):
-            st = _cabi.lib().mrg_gru_forward(gx.data_ptr(), whh.data_ptr(), _cabi.ptr(b_hh), y_ext.data_ptr(),
+            st = _cabi.lib().mrg_gru_forward(gx.data_ptr(), whh.data_ptr(), _cabi.ptr(whh_t), _cabi.ptr(b_hh), y_ext.data_ptr(),
                                              _cabi.ptr(reserve), T, B, H, 1 if train else 0,
                                              torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(st, "mrg_gru_forward")
