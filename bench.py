@@ -288,7 +288,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "frames_per_step": frames,
-                   "parallelism": f"dp{world} (batch sharded by sequence, one flat-bucket all-reduce)",
+                   "parallelism": f"dp{world} (batch sharded by sequence; flat gradient bucket, decoder / attention slices "
+                                  f"all-reduced during the encoders' BPTT, the rest in one trailing all-reduce)",
                    "cuda_graph": graph_note,
                    "l2": "no explicit flush: each step rewrites ~0.6 GB of reserve/activations, >> 126 MB L2"},
         "clocks": clocks,
