@@ -280,3 +280,24 @@ def test_metaformer_mirror_keeps_reference_keys_masks_and_arguments():
         gru(torch.zeros(1, 2, 8))                                         # and no CPU path
     with pytest.raises(ValueError):
         MixerLayerdFactory().build("conv", {})
+
+
+def test_attention_mask_rule_properties():
+    """AttentionMaskSpec (the rule the fused attention evaluates instead of reading the reference's mask tensor):
+    causal in both rate directions, every query sees at least the keys of its own frame, padding masks only
+    padded x padded pairs, and the [B, heads, L, S] view is a broadcast (no per-head copy)."""
+    from multimodalreactiongeneration_b200.attention import AttentionMaskSpec
+    for L, S, mode, rate in ((5, 15, 1, 3), (12, 4, 2, 3), (7, 7, 1, 1)):
+        pad_q = torch.zeros(2, L, dtype=torch.uint8)
+        pad_k = torch.zeros(2, S, dtype=torch.uint8)
+        pad_q[1, L - 2:] = 1
+        pad_k[1, S - 1:] = 1
+        m = AttentionMaskSpec(mode, rate, pad_q, pad_k).materialize(4)
+        assert m.shape == (2, 4, L, S) and m.stride(1) == 0                 # heads are a broadcast view
+        for i in range(L):
+            for j in range(S):
+                frame_q, frame_k = (i, j // rate) if mode == 1 else (i // rate, j)
+                want = frame_k > frame_q
+                assert bool(m[0, 0, i, j]) == want                          # unpadded sample: pure causality
+                assert bool(m[1, 0, i, j]) == (want or (bool(pad_q[1, i]) and bool(pad_k[1, j])))
+            assert not bool(m[0, 0, i].all())                               # no query is left without a key
