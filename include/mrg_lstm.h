@@ -59,6 +59,8 @@ extern "C" {
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that
                                   accumulate straight into the trainer's flat gradient bucket            */
 #define MRG_F_GEMM_V1    128   /* use the first-generation tensor-core GEMM (both operands in shared memory)  */
+#define MRG_F_BWD_NO_WGRAD   2048  /* backward: BPTT + bias sums + dX only (leaves d(pre-activations) in `gates`)    */
+#define MRG_F_BWD_WGRAD_ONLY 4096  /* backward: only dW_ih / dW_hh from a previous NO_WGRAD call (any stream)        */
 #define MRG_F_GEMM_V3    512   /* force the persistent (third-generation) GEMM; MRG_F_GEMM_V2 1024 forces the second  */
 #define MRG_F_GEMM_V2   1024
 #define MRG_F_REC_V1      64   /* use the first-generation cluster kernels (kept for A/B measurements)  */

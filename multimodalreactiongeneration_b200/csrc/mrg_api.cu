@@ -208,10 +208,15 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   r.db_part = db_part;
   r.T = T; r.B = B; r.H = H; r.D = D;
   r.cluster_budget = (flags >> 16) & 0xFF;
-  int e;
+  int e = 0;
+  // two-phase backward: MRG_F_BWD_NO_WGRAD = BPTT + bias sums + dX (what the previous layer waits for),
+  // MRG_F_BWD_WGRAD_ONLY = the two weight-gradient GEMMs from the d(pre-activations) an earlier NO_WGRAD call left in
+  // `gates` (the caller may queue it on another stream so that it overlaps the previous layer's BPTT)
+  const bool do_rec = !(flags & MRG_F_BWD_WGRAD_ONLY), do_wgrad = !(flags & MRG_F_BWD_NO_WGRAD);
   bool pointwise = (T == 1) && (flags & MRG_F_ZERO_STATE);
   for (int d = 0; d < D; ++d) pointwise = pointwise && !g[d].dh0 && !g[d].dc0;
-  if (pointwise) e = cell_zero_state_backward(gates, c_ext, dy, dh_n, dc_n, db_part, B, H, D, stream);
+  if (!do_rec) e = 0;
+  else if (pointwise) e = cell_zero_state_backward(gates, c_ext, dy, dh_n, dc_n, db_part, B, H, D, stream);
   else if (!(flags & (MRG_F_GENERIC_REC | MRG_F_REC_V1)) && rec2_supported(H)) e = rec_backward_cluster2(r, stream);
   else if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) e = rec_backward_cluster(r, stream);
   else e = rec_backward_generic(r, stream);
@@ -220,9 +225,9 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   const size_t slot = (size_t)B * H;
   for (int d = 0; d < D; ++d) {
     const float* dpre = gates + (size_t)d * T * B * 4 * H;
-    if (g[d].db)
+    if (g[d].db && do_rec)
       if ((e = colsum_deinterleave(db_part + (size_t)d * B * 4 * H, g[d].db, B, H, acc_b, stream))) return e;
-    if (g[d].dw_ih) {
+    if (g[d].dw_ih && do_wgrad) {
       GemmArgs m = {};
       m.a = dpre; m.a_sm = 1; m.a_sk = 4 * H;
       m.b = x; m.b_sk = I; m.b_sn = 1;
@@ -231,7 +236,8 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       m.accumulate = acc; m.row_deinterleave_H = H;
       if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
     }
-    if (g[d].dw_hh && pointwise) {  // h_prev = 0: no contribution
+    if (!do_wgrad) {
+    } else if (g[d].dw_hh && pointwise) {  // h_prev = 0: no contribution
       if (!acc) MRG_CUDA_CHECK(cudaMemsetAsync(g[d].dw_hh, 0, (size_t)4 * H * H * sizeof(float), stream));
     } else if (g[d].dw_hh) {
       const float* hprev = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : slot);
@@ -243,7 +249,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       m.accumulate = acc; m.row_deinterleave_H = H;
       if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
     }
-    if (dx) {
+    if (dx && do_rec) {
       GemmArgs m = {};
       m.a = dpre; m.a_sm = 4 * H; m.a_sk = 1;
       m.b = w_pack + (size_t)d * 4 * H * I; m.b_sk = I; m.b_sn = 1;

@@ -83,6 +83,41 @@ def set_precision(mode: str) -> None:
     _PRECISION["mode"] = mode
 
 
+# Weight-gradient overlap: inside ``with wgrad_overlap():`` (the trainer wraps ``loss.backward()`` in it) a layer's backward
+# is issued in two phases — BPTT + bias sums + dX on the node's own stream (what the previous layer's BPTT waits for), the
+# two weight-gradient GEMMs on a side stream, where they share the GPU with that next BPTT kernel (a cluster kernel leaves
+# 28 SMs idle) instead of delaying it.  Only when the gradients go straight into the trainer's flat bucket (nobody reads
+# them before the join at the end of the context).
+_WGRAD = {"on": False, "pending": [], "streams": {}}
+
+
+def _wgrad_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    st = _WGRAD["streams"].get(key)
+    if st is None:
+        st = _WGRAD["streams"][key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def join_wgrad_streams() -> None:
+    """The current stream waits for every weight-gradient GEMM queued on a side stream so far."""
+    for side in _WGRAD["pending"]:
+        torch.cuda.current_stream(side.device).wait_stream(side)
+    _WGRAD["pending"] = []
+
+
+class wgrad_overlap:
+    def __enter__(self):
+        self.prev = _WGRAD["on"]
+        _WGRAD["on"] = os.environ.get("MRG_WGRAD_OVERLAP", "1") != "0"
+        return self
+
+    def __exit__(self, *exc):
+        _WGRAD["on"] = self.prev
+        join_wgrad_streams()
+        return False
+
+
 class _LSTMLayerFn(torch.autograd.Function):
     """One nn.LSTM layer (1 or 2 directions), time-major, through the C-ABI."""
 
@@ -183,13 +218,28 @@ class _LSTMLayerFn(torch.autograd.Function):
             flags |= _cabi.F_ACC_WEIGHTS
         nbytes = L.mrg_lstm_workspace_bytes(T, B, I, H, D)
         ws = _workspace(dev, nbytes)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        main = torch.cuda.current_stream(dev)
+        overlap = fused and _WGRAD["on"] and T > 1
         with torch.cuda.device(dev):
             st = L.mrg_lstm_layer_backward(x.data_ptr(), dw, w_pack.data_ptr(), _cabi.ptr(dy),
                                            _cabi.ptr(dh_n), _cabi.ptr(dc_n), gates.data_ptr(),
                                            y_ext.data_ptr(), c_ext.data_ptr(), _cabi.ptr(dx), dg,
-                                           ws.data_ptr(), ws.numel(), T, B, I, H, D, flags, stream)
+                                           ws.data_ptr(), ws.numel(), T, B, I, H, D,
+                                           flags | (_cabi.F_BWD_NO_WGRAD if overlap else 0), main.cuda_stream)
         _cabi.check(st, "mrg_lstm_layer_backward")
+        if overlap:
+            side = _wgrad_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.device(dev), torch.cuda.stream(side):
+                ws2 = _workspace(dev, nbytes)   # keyed by the current (side) stream: its own split-K partials
+                st = L.mrg_lstm_layer_backward(x.data_ptr(), dw, w_pack.data_ptr(), None, None, None, gates.data_ptr(),
+                                               y_ext.data_ptr(), c_ext.data_ptr(), None, dg, ws2.data_ptr(), ws2.numel(),
+                                               T, B, I, H, D, flags | _cabi.F_BWD_WGRAD_ONLY, side.cuda_stream)
+            _cabi.check(st, "mrg_lstm_layer_backward (weight gradients)")
+            for t in (x, gates, y_ext):   # the allocator must not hand these out again before the side stream is done
+                t.record_stream(side)
+            if side not in _WGRAD["pending"]:
+                _WGRAD["pending"].append(side)
         ctx.saved = None
         return (dx, dh0, dc0, None, None, None, *grads)
 

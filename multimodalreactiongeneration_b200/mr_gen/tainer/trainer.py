@@ -185,6 +185,9 @@ class Trainer:
         if not self._in_backward or self._early_done[k] or not any(g is not None for g in grad_input):
             return
         a, b = self._early[k]
+        if self.bucket.flat.is_cuda:   # weight gradients of this slice may still be in flight on a side stream
+            from ...lstm import join_wgrad_streams
+            join_wgrad_streams()
         self._handles.append(dist.all_reduce(self.bucket.flat[a:b], op=dist.ReduceOp.SUM, async_op=True))
         self._early_done[k] = True
         self.n_early_all_reduces += 1
@@ -212,7 +215,12 @@ class Trainer:
             self.bucket.zero()
         loss = self.model.training_step(batch)["loss"]
         self._in_backward = True
-        loss.backward()
+        if loss.is_cuda:
+            from ...lstm import wgrad_overlap
+            with wgrad_overlap():   # weight-gradient GEMMs of the LSTM layers on side streams; joined on exit
+                loss.backward()
+        else:
+            loss.backward()
         self._in_backward = False
         world = self._all_reduce_rest()
         if self.flat_opt is not None:   # mean = SUM all-reduce, 1/world folded into the step; grads cleared by it
