@@ -209,31 +209,18 @@ class MultiModalMetaformer(nn.Module):
         main_modal_feature_dim = first(main_modal_feature_dim)
         main_mixer_type = first(main_mixer_type)
         main_cfg = [(main_mixer_type, first(main_mixer_configs))]
-        if isinstance(integrate_mixer_configs, dict):
-            integrate_mixer_configs = [integrate_mixer_configs]
-        integrate_mixer_configs = check_form_modal_num(
-            n_other, integrate_mixer_configs,
-            f"The length of integrate_mixer_configs must be equal to modal_num - 1."
-            f"modal_num: {modal_num}, integrate_mixer_configs: {len(integrate_mixer_configs)}")
-        integrate_cfg = [("mha", c) for c in integrate_mixer_configs]
-        if isinstance(other_modal_feature_dim, int):
-            other_modal_feature_dim = [other_modal_feature_dim]
-        other_modal_feature_dim = check_form_modal_num(
-            n_other, other_modal_feature_dim,
-            f"The length of other_modal_feature_dim must be equal to modal_num - 1."
-            f"modal_num: {modal_num}, other_modal_feature_dim: {len(other_modal_feature_dim)}")
-        if isinstance(other_mixer_type, str):
-            other_mixer_type = [other_mixer_type]
-        other_mixer_type = check_form_modal_num(
-            n_other, other_mixer_type,
-            f"The length of other_mixer_type must be equal to modal_num - 1."
-            f"modal_num: {modal_num}, other_mixer_type: {len(other_mixer_type)}")
-        if isinstance(other_mixer_configs, dict):
-            other_mixer_configs = [other_mixer_configs]
-        other_mixer_configs = check_form_modal_num(
-            n_other, other_mixer_configs,
-            f"The length of other_mixer_configs must be equal to modal_num - 1."
-            f"modal_num: {modal_num}, other_mixer_configs: {len(other_mixer_configs)}")
+        def per_other(value, name, scalar_types):
+            """one entry per non-main modality: a bare value is wrapped, a single entry is repeated"""
+            if isinstance(value, scalar_types):
+                value = [value]
+            return check_form_modal_num(
+                n_other, value, f"The length of {name} must be equal to modal_num - 1."
+                                f"modal_num: {modal_num}, {name}: {len(value)}")
+
+        integrate_cfg = [("mha", c) for c in per_other(integrate_mixer_configs, "integrate_mixer_configs", dict)]
+        other_modal_feature_dim = per_other(other_modal_feature_dim, "other_modal_feature_dim", int)
+        other_mixer_type = per_other(other_mixer_type, "other_mixer_type", str)
+        other_mixer_configs = per_other(other_mixer_configs, "other_mixer_configs", dict)
         other_cfg = [(other_mixer_type[i], other_mixer_configs[i]) for i in range(n_other)]
 
         self.modal_num = modal_num
