@@ -58,12 +58,8 @@ extern "C" {
                                   independent LSTM stacks (audio / motion encoders) run side by side on two streams */
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that
                                   accumulate straight into the trainer's flat gradient bucket            */
-#define MRG_F_GEMM_V1    128   /* use the first-generation tensor-core GEMM (both operands in shared memory)  */
 #define MRG_F_BWD_NO_WGRAD   2048  /* backward: BPTT + bias sums + dX only (leaves d(pre-activations) in `gates`)    */
 #define MRG_F_BWD_WGRAD_ONLY 4096  /* backward: only dW_ih / dW_hh from a previous NO_WGRAD call (any stream)        */
-#define MRG_F_GEMM_V3    512   /* force the persistent (third-generation) GEMM; MRG_F_GEMM_V2 1024 forces the second  */
-#define MRG_F_GEMM_V2   1024
-#define MRG_F_REC_V1      64   /* use the first-generation cluster kernels (kept for A/B measurements)  */
 #define MRG_F_ZERO_STATE  16   /* caller guarantees h0 = c0 = 0 (hx=None): with T == 1 the layer is a
                                   pointwise cell on the projection (no recurrence, W_hh inert) — the
                                   stateless predictor steps of the lstm_with_sampling rollout       */
@@ -146,7 +142,7 @@ int mrg_residual_layernorm_backward(const float* dout, long long d_s0, long long
 int mrg_philox_mask(uint64_t seed, uint64_t offset, float prob, int T, int B, int shared, uint8_t* out,
                     void* stream);
 
-/* out[N] (+)= column sums of x[M][N] (N % 4 == 0, x 16-byte aligned): the bias gradient of the Linear layers next
+/* out[N] (+)= column sums of x[M][N] (any N; float4 loads when N % 4 == 0 and x is 16-byte aligned): the bias gradient of the Linear layers next
  * to the LSTMs (LSTMModule.mixer, the bottleneck FFN, embed / projection layers).  Deterministic two-pass sum. */
 size_t mrg_colsum_workspace_bytes(int M, int N);
 int mrg_colsum(const float* x, float* out, int M, int N, int accumulate, void* workspace, size_t workspace_bytes,

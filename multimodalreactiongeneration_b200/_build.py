@@ -43,10 +43,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
+    live = {os.path.basename(s)[:-3] + ".o" for s in _sources()}
+    for stale in glob.glob(os.path.join(CSRC, "build", "*.o")):   # objects of deleted sources must not be linked
+        if os.path.basename(stale) not in live:
+            os.remove(stale)
     for src in _sources():
         obj = os.path.join(CSRC, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC, *flags, "-DMRG_HAVE_TC_GEMM" if os.path.exists(os.path.join(CSRC, "mrg_gemm_tc.cu")) else "-DMRG_NO_TC_GEMM",
-               "-c", src, "-o", obj]
+        cmd = [NVCC, *flags, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -61,7 +64,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc failed; see stderr")
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    # -cudart shared: torch already ships libcudart, so the library does not embed a second copy of the runtime
+    cmd = [NVCC, "-shared", "-cudart", "shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
     return LIB
 

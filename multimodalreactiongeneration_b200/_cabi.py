@@ -8,9 +8,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint8, c_uint6
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libmrg_b200.so")
 
-F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE, F_ZERO_STATE, F_TF32, F_REC_V1, F_GEMM_V1 = 1, 2, 4, 8, 16, 32, 64, 128
+F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE, F_ZERO_STATE, F_TF32 = 1, 2, 4, 8, 16, 32
 F_ACC_WEIGHTS = 256
-F_GEMM_V3, F_GEMM_V2 = 512, 1024
 F_BWD_NO_WGRAD, F_BWD_WGRAD_ONLY = 2048, 4096
 
 EXPORTS = (

@@ -11,14 +11,13 @@ no masks) and mr_gen/model/utils/for_sequential.py:25-50 (lstmformer's integrato
 names / shapes / init order and ``state_dict`` keys are ``nn.MultiheadAttention``'s (``in_proj_weight`` or
 ``q_/k_/v_proj_weight``, ``in_proj_bias``, ``out_proj.*``).
 
-Which path runs: head_dim 32 or 64, no attention dropout, mask = None or an ``AttentionMaskSpec`` -> fused kernels;
-an explicit mask TENSOR, another head_dim or dropout > 0 -> ``F.scaled_dot_product_attention`` (torch library
-kernel) between the same tcgen05 projections; argument combinations the reference does not use on this path
-(attention weights requested, key padding masks, ``bias_k`` / ``add_zero_attn``, time-major layout) are delegated to
-``nn.MultiheadAttention.forward`` unchanged.  ``MRG_FUSED_ATTENTION=0`` forces the SDPA path (A/B measurements)."""
+Which path runs: ONE — the fused kernels.  Head dims other than 32 / 64 are zero-padded per head to the next built
+width (zero columns change neither the scores nor the outputs; the scale stays 1/sqrt(true head_dim)), mask = None
+or an ``AttentionMaskSpec``.  There is no dispatch to a torch library kernel: an explicit mask TENSOR, attention
+dropout in training mode, head_dim > 64, and the argument combinations the reference does not use on this path
+(attention weights requested, key padding masks, ``bias_k`` / ``add_zero_attn``, time-major layout, CPU tensors)
+raise ``NotImplementedError`` / ``RuntimeError``."""
 from __future__ import annotations
-
-import os
 
 import torch
 from torch import nn
@@ -62,7 +61,7 @@ class _AttentionFn(torch.autograd.Function):
     (one projection GEMM) and its gradient comes back fused as well."""
 
     @staticmethod
-    def forward(ctx, q, k, v, nh, spec):
+    def forward(ctx, q, k, v, nh, spec, scale=None):
         B, Tq, E = q.shape
         fused = v is None
         q, ldq = _rows(q)
@@ -77,7 +76,8 @@ class _AttentionFn(torch.autograd.Function):
         o = torch.empty((B, Tq, E), dtype=torch.float32, device=q.device)
         lse = torch.empty((B, nh, Tq), dtype=torch.float32, device=q.device)
         mode, rate, pq, pk = (0, 1, None, None) if spec is None else (spec.mode, spec.rate, spec.pad_q, spec.pad_k)
-        scale = float(hd) ** -0.5
+        if scale is None:
+            scale = float(hd) ** -0.5
         with torch.cuda.device(q.device):
             st = _cabi.lib().mrg_attention_forward(
                 q.data_ptr(), ldq, kk.data_ptr(), ldk, vv.data_ptr(), ldv, o.data_ptr(), E, lse.data_ptr(), B, nh, Tq,
@@ -110,41 +110,50 @@ class _AttentionFn(torch.autograd.Function):
                 Tq, Tk, hd, scale, mode, rate, _cabi.ptr(pq), _cabi.ptr(pk),
                 torch.cuda.current_stream(o.device).cuda_stream)
         _cabi.check(st, "mrg_attention_backward")
-        return (dq, dkv, None, None, None) if fused else (dq, dk, dv, None, None)
+        return (dq, dkv, None, None, None, None) if fused else (dq, dk, dv, None, None, None)
 
 
 def fused_attention(q, k, v, num_heads: int, mask: AttentionMaskSpec = None):
     """q [B, Tq, E], k / v [B, Tk, E] (or ``k`` = fused [B, Tk, 2E] and ``v`` = None) -> [B, Tq, E]; fp32 CUDA only."""
     if not (q.is_cuda and q.dtype == torch.float32):
         raise RuntimeError("fused_attention: fp32 CUDA tensors only (no CPU path)")
-    return _AttentionFn.apply(q, k, v, num_heads, mask)
+    return _AttentionFn.apply(q, k, v, num_heads, mask, None)
 
 
-def _fused_ok(hd: int, dropout: float, training: bool, attn_mask) -> bool:
-    return (hd in (32, 64) and not (training and dropout > 0.0)
-            and (attn_mask is None or isinstance(attn_mask, AttentionMaskSpec))
-            and os.environ.get("MRG_FUSED_ATTENTION", "1") != "0")
+def _padded_head_dim(hd: int) -> int:
+    if hd <= 32:
+        return 32
+    if hd <= 64:
+        return 64
+    raise NotImplementedError(f"B200MultiheadAttention: head_dim {hd} > 64 is not built")
+
+
+def _pad_heads(t: torch.Tensor, nh: int, hd: int, hdp: int) -> torch.Tensor:
+    """[B, T, nh*hd] -> [B, T, nh*hdp] with zero columns appended to every head."""
+    B, T, _ = t.shape
+    return F.pad(t.reshape(B, T, nh, hd), (0, hdp - hd)).reshape(B, T, nh * hdp)
 
 
 class B200MultiheadAttention(nn.MultiheadAttention):
     def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None,
                 average_attn_weights=True, is_causal=False):
-        plain = (self.batch_first and not need_weights and key_padding_mask is None
-                 and (attn_mask is None or isinstance(attn_mask, AttentionMaskSpec) or attn_mask.dim() in (2, 3, 4))
-                 and not is_causal
-                 and self.bias_k is None and self.bias_v is None and not self.add_zero_attn
-                 and query.dim() == 3 and query.is_cuda and query.dtype == torch.float32)
-        if not plain:
-            if isinstance(attn_mask, AttentionMaskSpec):
-                attn_mask = attn_mask.materialize(self.num_heads).reshape(-1, query.shape[-2], key.shape[-2])
-            return super().forward(query, key, value, key_padding_mask=key_padding_mask, need_weights=need_weights,
-                                   attn_mask=attn_mask, average_attn_weights=average_attn_weights,
-                                   is_causal=is_causal)
+        if not (query.is_cuda and query.dtype == torch.float32):
+            raise RuntimeError("B200MultiheadAttention has no CPU path: fp32 CUDA tensors only")
+        if attn_mask is not None and not isinstance(attn_mask, AttentionMaskSpec):
+            raise NotImplementedError("B200MultiheadAttention: pass the mask as an AttentionMaskSpec (the rule of "
+                                      "multi_modal_metaformer.py:32-79); mask tensors are not read")
+        if not (self.batch_first and not need_weights and key_padding_mask is None and not is_causal
+                and self.bias_k is None and self.bias_v is None and not self.add_zero_attn and query.dim() == 3):
+            raise NotImplementedError("B200MultiheadAttention: only the reference's call form is built (batch_first, "
+                                      "need_weights=False, no key_padding_mask / bias_kv / zero_attn / is_causal)")
+        if self.training and self.dropout > 0.0:
+            raise NotImplementedError("B200MultiheadAttention: attention dropout is not built (the reference "
+                                      "configurations use dropout 0)")
         E, nh = self.embed_dim, self.num_heads
         hd = E // nh
+        hdp = _padded_head_dim(hd)
         b = self.in_proj_bias
         bq, bk, bv = (None, None, None) if b is None else (b[:E], b[E:2 * E], b[2 * E:])
-        fused = _fused_ok(hd, self.dropout, self.training, attn_mask)
         kv = None
         if self._qkv_same_embed_dim:
             w = self.in_proj_weight
@@ -159,24 +168,13 @@ class B200MultiheadAttention(nn.MultiheadAttention):
             q = _LinearFn.apply(query, self.q_proj_weight, bq)
             k = _LinearFn.apply(key, self.k_proj_weight, bk)
             v = _LinearFn.apply(value, self.v_proj_weight, bv)
-        if fused:
-            att = _AttentionFn.apply(q, kv, None, nh, attn_mask) if kv is not None else \
-                _AttentionFn.apply(q, k, v, nh, attn_mask)
-            return _LinearFn.apply(att, self.out_proj.weight, self.out_proj.bias), None
-        if isinstance(attn_mask, AttentionMaskSpec):
-            attn_mask = attn_mask.materialize(nh)
-        B, Tq, Tk = query.shape[0], query.shape[1], key.shape[1]
-        q = q.reshape(B, Tq, nh, hd).transpose(1, 2)
-        k = k.reshape(B, Tk, nh, hd).transpose(1, 2)
-        v = v.reshape(B, Tk, nh, hd).transpose(1, 2)
-        sdpa_mask = None
-        if attn_mask is not None:
-            # [L,S] | [B*heads,L,S] (nn.MultiheadAttention's forms) | [B, 1 or heads, L, S] (broadcast view: no
-            # per-head copy is made)
-            m = attn_mask.reshape(B, nh, Tq, Tk) if attn_mask.dim() == 3 else attn_mask
-            # nn.MultiheadAttention: bool True = "not allowed", float = additive; SDPA: bool True = "takes part"
-            sdpa_mask = ~m if m.dtype == torch.bool else m.to(q.dtype)
-        att = F.scaled_dot_product_attention(q, k, v, attn_mask=sdpa_mask,
-                                             dropout_p=self.dropout if self.training else 0.0)
-        att = att.transpose(1, 2).reshape(B, Tq, E)
+        if hdp != hd:
+            q, k, v = (_pad_heads(t, nh, hd, hdp) for t in (q, k, v))
+            att = _AttentionFn.apply(q, k, v, nh, attn_mask, float(hd) ** -0.5)
+            B, Tq = att.shape[:2]
+            att = att.reshape(B, Tq, nh, hdp)[..., :hd].reshape(B, Tq, E)
+        elif kv is not None:
+            att = _AttentionFn.apply(q, kv, None, nh, attn_mask, None)
+        else:
+            att = _AttentionFn.apply(q, k, v, nh, attn_mask, None)
         return _LinearFn.apply(att, self.out_proj.weight, self.out_proj.bias), None

@@ -6,9 +6,7 @@
 #include "mrg_common.cuh"
 
 namespace mrg {
-int gemm_tc(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-int gemm_tc3(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 bool gemm_tc_supported(const GemmArgs& g);
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 
@@ -17,28 +15,14 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int run_gemm(const GemmArgs& g_in, void* ws, size_t ws_bytes, int flags, cudaStream_t stream) {
   GemmArgs g = g_in;
   g.single_pass = (flags & MRG_F_TF32) ? 1 : 0;
-#ifdef MRG_HAVE_TC_GEMM
-  if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) {
-    if (flags & MRG_F_GEMM_V1) return gemm_tc(g, ws, ws_bytes, stream);
-    static int v3 = -1;  // MRG_GEMM_V3: 1 = persistent kernel for every shape, 0 = never, unset = per-shape choice
-    if (v3 < 0) {
-      const char* e = getenv("MRG_GEMM_V3");
-      v3 = e ? (e[0] == '1' ? 1 : 0) : 2;
-    }
-    if (flags & MRG_F_GEMM_V2) return gemm_tc2(g, ws, ws_bytes, stream);
-    if (v3 == 1 || (flags & MRG_F_GEMM_V3)) return gemm_tc3(g, ws, ws_bytes, stream);
-    return gemm_tc2(g, ws, ws_bytes, stream);
-  }
-#endif
+  if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) return gemm_tc2(g, ws, ws_bytes, stream);
   return gemm_simt(g, ws, ws_bytes, stream);
 }
 
 static size_t gemm_ws(int M, int N, int K) {
   size_t s = gemm_simt_workspace_bytes(M, N, K);
-#ifdef MRG_HAVE_TC_GEMM
   const size_t t = gemm_tc_workspace_bytes(M, N, K);
   if (t > s) s = t;
-#endif
   return s;
 }
 
@@ -168,8 +152,7 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   r.train = (flags & MRG_F_TRAIN) ? 1 : 0;
   r.trace = debug_trace_buffer();
   r.cluster_budget = (flags >> 16) & 0xFF;
-  if (!(flags & (MRG_F_GENERIC_REC | MRG_F_REC_V1)) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
-  if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) return rec_forward_cluster(r, stream);
+  if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
   return rec_forward_generic(r, stream);
 }
 
@@ -217,8 +200,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   for (int d = 0; d < D; ++d) pointwise = pointwise && !g[d].dh0 && !g[d].dc0;
   if (!do_rec) e = 0;
   else if (pointwise) e = cell_zero_state_backward(gates, c_ext, dy, dh_n, dc_n, db_part, B, H, D, stream);
-  else if (!(flags & (MRG_F_GENERIC_REC | MRG_F_REC_V1)) && rec2_supported(H)) e = rec_backward_cluster2(r, stream);
-  else if (!(flags & MRG_F_GENERIC_REC) && rec_cluster_supported(H)) e = rec_backward_cluster(r, stream);
+  else if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) e = rec_backward_cluster2(r, stream);
   else e = rec_backward_generic(r, stream);
   if (e) return e;
 

@@ -467,16 +467,7 @@ static int attn_check(const char* who, const AttnArgs& a, int hd) {
   MRG_REQUIRE((a.pad_q == nullptr) == (a.pad_k == nullptr), "%s: pad_q and pad_k go together", who);
   return 0;
 }
-// The CUDA-core kernels of this file are the default: measured on B200 (profiles/r1d_attention.txt) the warp-level
-// 3xTF32 tensor-core variant (mrg_attention_tc.cu, MRG_ATTENTION_TC=1) is SLOWER — legacy mma.sync tf32 throughput
-// plus the per-fragment hi/lo splitting cost more than the FMA work they replace at d = 32 / 64.
 static int attn_dispatch(const AttnArgs& a, int hd, int backward, cudaStream_t stream) {
-  static int tc = -1;
-  if (tc < 0) {
-    const char* e = getenv("MRG_ATTENTION_TC");
-    tc = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (tc) return attn_tc_launch(a, hd, backward, stream);
   return hd == 32 ? attn_launch<32>(a, backward, stream) : attn_launch<64>(a, backward, stream);
 }
 #define AT_ALIGNED(p, ld) ((p) != nullptr && (((uintptr_t)(p)) & 15) == 0 && (ld) % 4 == 0 && (ld) >= nh * hd)

@@ -260,8 +260,6 @@ struct RecArgs {
 };
 unsigned long long* debug_trace_buffer();
 int rec_forward_generic(const RecArgs& a, cudaStream_t stream);
-int rec_forward_cluster(const RecArgs& a, cudaStream_t stream);  // H in {128, 256}
-bool rec_cluster_supported(int H);
 
 struct RecBwdArgs {
   float* gates;         // in: gates, out: dpre   [D][T][B][H][4]
@@ -278,9 +276,7 @@ struct RecBwdArgs {
   int cluster_budget;   // same meaning as in RecArgs
 };
 int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
-int rec_backward_cluster(const RecBwdArgs& a, cudaStream_t stream);
-// second-generation cluster kernels (chunk-pipelined, H in {128, 256}); the first generation stays
-// selectable with MRG_F_REC_V1 for A/B measurements
+// cluster kernels (chunk-pipelined, H in {128, 256})
 int rec_forward_cluster2(const RecArgs& a, cudaStream_t stream);
 int rec_backward_cluster2(const RecBwdArgs& a, cudaStream_t stream);
 bool rec2_supported(int H);
@@ -295,7 +291,7 @@ int cell_zero_state_backward(float* gates, const float* c_ext, const float* dy, 
 
 int colsum_deinterleave(const float* part, float* db, int B, int H, int accumulate,
                         cudaStream_t stream);
-// fused attention (mrg_attention.cu: CUDA-core kernels, mrg_attention_tc.cu: tensor-core kernels)
+// fused attention (mrg_attention.cu)
 struct AttnArgs {
   const float *q, *k, *v;
   float* o;
@@ -309,9 +305,6 @@ struct AttnArgs {
   int mask_mode, rate;
   const unsigned char *pad_q, *pad_k;  // [B, Tq], [B, Tk] or both null
 };
-int attn_tc_launch(const AttnArgs& a, int hd, int backward, cudaStream_t stream);
-
-int max_active_clusters(int H);
 
 // launch accounting / live kernel timing (bench.py's gpu_launches and roofline numbers)
 void count_launch(int n = 1);

@@ -287,6 +287,27 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
     if (n + 3 < N) o[n + 3] = s.w;
   }
 }
+// pass 1 for rows that are not float4-addressable (N % 4 != 0 or an unaligned base: the 6- / 18-wide pose heads):
+// 32 columns x 8 row phases per block, scalar loads
+__global__ void __launch_bounds__(256) colsum_slab_scalar_kernel(const float* __restrict__ x,
+                                                                 float* __restrict__ partial, int M, int N) {
+  __shared__ float red[8][33];
+  const int c = threadIdx.x & 31, rp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  const int m0 = blockIdx.y * COLSUM_ROWS;
+  const int m1 = min(M, m0 + COLSUM_ROWS);
+  float acc = 0.f;
+  if (n < N)
+    for (int m = m0 + rp; m < m1; m += 8) acc += __ldg(x + (size_t)m * N + n);
+  red[rp][c] = acc;
+  __syncthreads();
+  if (rp == 0 && n < N) {
+    float s = red[0][c];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][c];
+    partial[(size_t)blockIdx.y * N + n] = s;
+  }
+}
 // pass 2: 32 columns x 8 slab lanes per block; lane l adds slabs l, l+8, ... then the 8 lanes are added in order
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
                                                            int slabs, int N, int accumulate) {
@@ -316,7 +337,6 @@ extern "C" int mrg_colsum(const float* x, float* out, int M, int N, int accumula
                           size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MRG_REQUIRE(out && M >= 0 && N > 0 && (x || M == 0), "mrg_colsum: bad arguments");
-  MRG_REQUIRE(((uintptr_t)x & 15) == 0, "mrg_colsum: x must be 16-byte aligned");
   if (M == 0) {
     if (!accumulate) MRG_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), stream));
     return 0;
@@ -327,8 +347,10 @@ extern "C" int mrg_colsum(const float* x, float* out, int M, int N, int accumula
   }
   const int slabs = (M + mrg::COLSUM_ROWS - 1) / mrg::COLSUM_ROWS;
   mrg::count_launch(2);
-  MRG_REQUIRE(N % 4 == 0, "mrg_colsum: N must be a multiple of 4 (16-byte aligned rows)");
-  mrg::colsum_slab_kernel<<<dim3((N + 255) / 256, slabs), 256, 0, stream>>>(x, (float*)workspace, M, N);
+  if (N % 4 == 0 && ((uintptr_t)x & 15) == 0)
+    mrg::colsum_slab_kernel<<<dim3((N + 255) / 256, slabs), 256, 0, stream>>>(x, (float*)workspace, M, N);
+  else
+    mrg::colsum_slab_scalar_kernel<<<dim3((N + 31) / 32, slabs), 256, 0, stream>>>(x, (float*)workspace, M, N);
   MRG_CUDA_CHECK(cudaGetLastError());
   mrg::colsum_final_kernel<<<(N + 31) / 32, 256, 0, stream>>>((const float*)workspace, out, slabs, N, accumulate);
   MRG_CUDA_CHECK(cudaGetLastError());

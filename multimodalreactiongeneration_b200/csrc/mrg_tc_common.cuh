@@ -7,10 +7,7 @@
 namespace mrg {
 
 constexpr int TBM = 128, TBN = 128, TBK = 32;
-constexpr int STAGES = 3;   // v1 kernel (A and B both converted in shared memory)
 constexpr int TILE_BYTES = TBM * TBK * 4;                 // 16 KB per operand tile
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;               // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct TcParams {
   int M, N, K;

@@ -26,15 +26,9 @@ def _gemm(a, a_sm, a_sk, b, b_sk, b_sn, bias, c, M, N, K, flags, accumulate=0):
 
 
 def _colsum(x2, into=None):
-    """Column sums of a contiguous [M, N] fp32 matrix (bias gradient) through the C-ABI; torch only for N % 4 != 0.
+    """Column sums of a contiguous [M, N] fp32 matrix (bias gradient) through the C-ABI (``mrg_colsum``).
     ``into``: accumulate into this [N] tensor instead of returning a new one."""
     M, N = x2.shape
-    if N % 4 != 0 or x2.data_ptr() % 16 != 0:
-        s = x2.sum(dim=0)
-        if into is None:
-            return s
-        into.add_(s)
-        return None
     L = _cabi.lib()
     dev = x2.device
     out = torch.empty(N, dtype=torch.float32, device=dev) if into is None else into
@@ -50,7 +44,12 @@ def fused_grad_target(p):
     """The trainer's flat gradient bucket owns ``p.grad`` and is cleared by the optimizer kernel: weight-gradient
     kernels may then ADD straight into it (and return no gradient to autograd) instead of writing a temporary that
     autograd adds with one more launch per parameter."""
-    if getattr(p, "_mrg_grad_fused", False) and p.grad is not None and p.grad.is_contiguous():
+    if (getattr(p, "_mrg_grad_fused", False) and p.requires_grad and p.grad is not None
+            and p.grad.is_contiguous()):
+        # autograd never sees this write, so it cannot order it: remember the stream it is queued on and let
+        # ``lstm.join_wgrad_streams`` (the trainer, before the all-reduce / optimizer) wait for it explicitly
+        from .lstm import note_fused_write
+        note_fused_write(p.grad.device)
         return p.grad
     return None
 

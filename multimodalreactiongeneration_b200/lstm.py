@@ -38,10 +38,6 @@ def _default_flags() -> int:
     f = 0
     if os.environ.get("MRG_GENERIC_REC", "0") == "1":
         f |= _cabi.F_GENERIC_REC
-    if os.environ.get("MRG_GEMM_V1", "0") == "1":
-        f |= _cabi.F_GEMM_V1
-    if os.environ.get("MRG_REC_V1", "0") == "1":
-        f |= _cabi.F_REC_V1
     if os.environ.get("MRG_SIMT_GEMM", "0") == "1":
         f |= _cabi.F_SIMT_GEMM
     if _PRECISION["mode"] == "tf32":
@@ -99,10 +95,22 @@ def _wgrad_stream(dev: torch.device) -> torch.cuda.Stream:
     return st
 
 
+def note_fused_write(dev: torch.device) -> None:
+    """A kernel that adds into the trainer's flat gradient bucket behind autograd's back is being queued on the
+    current stream of ``dev`` (``linear.fused_grad_target``): record the stream for ``join_wgrad_streams``."""
+    st = torch.cuda.current_stream(dev)
+    if all(st != s for s in _WGRAD["pending"]):
+        _WGRAD["pending"].append(st)
+
+
 def join_wgrad_streams() -> None:
-    """The current stream waits for every weight-gradient GEMM queued on a side stream so far."""
+    """The current stream waits for every stream that has queued a write into the flat gradient bucket so far:
+    the side streams of the weight-gradient GEMMs and any stream a fused weight-gradient kernel ran on (e.g. the
+    second encoder stream of SimpleLSTM) — an explicit join, not the autograd engine's leaf-stream sync."""
     for side in _WGRAD["pending"]:
-        torch.cuda.current_stream(side.device).wait_stream(side)
+        cur = torch.cuda.current_stream(side.device)
+        if cur != side:
+            cur.wait_stream(side)
     _WGRAD["pending"] = []
 
 

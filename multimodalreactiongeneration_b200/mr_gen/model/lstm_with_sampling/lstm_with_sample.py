@@ -25,7 +25,7 @@ from typing import List, Optional, Tuple
 import torch
 from torch import nn
 
-from ....linear import B200Linear
+from ....linear import B200Linear, _LinearFn
 
 from ....import _cabi
 from ...utils.lightning_shim import LightningModule
@@ -36,6 +36,11 @@ from ..utils.lstm_block import LSTMLayerd
 from ..utils.values import PADDING_VALUE
 
 InputTypes = Tuple[torch.Tensor, torch.Tensor]
+
+
+def _linear(x, weight, bias):
+    """``x @ weight.T + bias`` with a SLICE of a registered weight, on the library's GEMM (no cuBLAS)."""
+    return _LinearFn.apply(x, weight, bias)
 
 
 def philox_sampling_mask(seed: int, offset: int, prob: float, length: int, batch: int, device,
@@ -220,7 +225,7 @@ class LSTMwithSample(LightningModule):
         sampled = sampled[:, lead_frames:]                     # [B, T, Hs]
         Hs = sampled.shape[-1]
         W, bias = self.feature_projection.weight, self.feature_projection.bias
-        base = torch.nn.functional.linear(torch.cat([sampled, mp], dim=-1), W[:, :Hs + P], bias)  # [B,T,Hd]
+        base = _linear(torch.cat([sampled, mp], dim=-1), W[:, :Hs + P], bias)  # [B,T,Hd]
         W_prev = W[:, Hs + P:]                                 # [Hd, P]
         base = base.reshape(B * T, -1)
         # --- feedback depth of every (b, t) -----------------------------------------------------
@@ -245,7 +250,7 @@ class LSTMwithSample(LightningModule):
                 continue
             idx = order[starts[d]:starts[d + 1]]
             prev = gt_prev.index_select(0, idx) if d == 0 else outs[d - 1].index_select(0, slot[idx - 1])
-            x = base.index_select(0, idx) + torch.nn.functional.linear(prev, W_prev)
+            x = base.index_select(0, idx) + _linear(prev, W_prev, None)
             h, _ = self.layerd_lstm(x.unsqueeze(1), None)       # stateless predictor blocks (Q2), T = 1
             outs.append(self.feed_forward(h).squeeze(1))
         inverse = torch.empty_like(order)

@@ -1,6 +1,6 @@
 """Mirror of mr_gen/model/utils/multi_modal_att.py — cross-modal nn.MultiheadAttention stack.
 The projections around the attention run on the library's tcgen05 GEMM (``B200MultiheadAttention``,
-``B200Linear``); softmax(QK^T)V is torch's SDPA (fused attention is "next")."""
+``B200Linear``); softmax(QK^T)V runs on the fused attention kernels (``mrg_attention_forward / _backward``)."""
 from torch import nn
 
 from ....attention import B200MultiheadAttention

@@ -210,18 +210,27 @@ class Trainer:
         self._early_done = [False] * len(self._early)
         return world
 
-    def train_step(self, batch) -> torch.Tensor:
+    def forward_backward(self, batch) -> torch.Tensor:
+        """``training_step`` + backward into the flat bucket (this rank's gradients, not yet averaged).  On CUDA the
+        weight-gradient GEMMs of the LSTM layers run on side streams; every stream that wrote into the bucket
+        (those side streams, the second encoder stream of SimpleLSTM) is joined explicitly before returning."""
         if self.flat_opt is None:
             self.bucket.zero()
         loss = self.model.training_step(batch)["loss"]
         self._in_backward = True
-        if loss.is_cuda:
-            from ...lstm import wgrad_overlap
-            with wgrad_overlap():   # weight-gradient GEMMs of the LSTM layers on side streams; joined on exit
+        try:
+            if loss.is_cuda:
+                from ...lstm import wgrad_overlap
+                with wgrad_overlap():   # joins the side streams and every fused-write stream on exit
+                    loss.backward()
+            else:
                 loss.backward()
-        else:
-            loss.backward()
-        self._in_backward = False
+        finally:
+            self._in_backward = False
+        return loss.detach()
+
+    def train_step(self, batch) -> torch.Tensor:
+        loss = self.forward_backward(batch)
         world = self._all_reduce_rest()
         if self.flat_opt is not None:   # mean = SUM all-reduce, 1/world folded into the step; grads cleared by it
             self.flat_opt.step(grad_scale=1.0 / world, zero_grad=True)
@@ -230,7 +239,7 @@ class Trainer:
                 self.bucket.flat.mul_(1.0 / world)
             self.optimizer.step()
         self.global_step += 1
-        return loss.detach()
+        return loss
 
     # ------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole step (zero bucket -> fwd -> bwd -> all-reduce -> optimizer).
@@ -267,6 +276,30 @@ class Trainer:
         self._graph = None
         self._static_loss = None
         self._static_batch = None
+
+    def close(self, destroy_process_group: bool = True, timeout_s: float = 30.0) -> None:
+        """Orderly shutdown: drop the captured step (NCCL keeps communicators alive for a live graph), drain the
+        device, meet the other ranks, then tear the process group down.  The teardown has been seen to block at 8
+        ranks after graph-captured collectives; a watchdog ends the process (exit code 0, all results are out) if it
+        does not return within ``timeout_s``."""
+        if getattr(self, "_graph", None) is not None:
+            self.release_cuda_graph()
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier()
+        if not destroy_process_group:
+            return
+        import sys
+        import threading
+        sys.stdout.flush()
+        sys.stderr.flush()
+        watchdog = threading.Timer(timeout_s, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
     def train_step_graphed(self, batch) -> torch.Tensor:
         for dst, src in zip(self._static_batch, batch):

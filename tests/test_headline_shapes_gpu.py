@@ -1,0 +1,172 @@
+"""GPU parity on the shapes that bench.py actually times ("What's weak" 1-3).
+
+* ``B200LSTM(256, 256, 2)`` forward AND backward at B=64 with T=300 (cfg 2) and T=900 (cfg 3) against fp64
+  ``torch.nn.LSTM`` — the launch the bench times (``rec_fwd2/rec_bwd2<256, 4>``), also with half the clusters
+  (``cluster_budget(7)``: the two encoder stacks of SimpleLSTM run side by side like that);
+* the exact bench model (``simple_lstm_cfg(256, 2)``, B=64 x 300): one training step, loss and EVERY parameter
+  gradient, against ``oracle.ref_port.simple_lstm_training_step`` in fp64 on the CPU, through ``Trainer.train_step``
+  with the weight-gradient overlap and the two-stream encoders on and off (the flat bucket holds the gradients);
+* ``LSTMwithSample`` at H=256 / sampler 128, T=300, one padded row, scheduled sampling at rate 0.5 and 1.0 (free
+  running) against ``oracle.ref_port.lws_rollout`` (the reference's step-by-step loop) — not against itself;
+* the 2^31 index guard of the cluster kernels.
+
+Tolerances: BASELINE.json north_star — hidden states 1e-5 norm-relative per step, loss / gradients 1e-4."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _per_step_err(y, ref):
+    y, ref = y.double().cpu(), ref.double().cpu()
+    num = (y - ref).abs().amax(dim=(0, 2))
+    den = ref.abs().amax(dim=(0, 2)).clamp_min(1e-30)
+    return float((num / den).max())
+
+
+@pytest.mark.parametrize("T,budget", [(300, 0), (300, 7), (900, 0)])
+def test_two_layer_lstm_gradients_at_benchmark_length(T, budget):
+    from multimodalreactiongeneration_b200 import B200LSTM
+    from multimodalreactiongeneration_b200.lstm import cluster_budget
+    B, H = 64, 256
+    torch.manual_seed(0)
+    ref = torch.nn.LSTM(H, H, 2, batch_first=True).double()
+    mine = B200LSTM(H, H, 2, batch_first=True)
+    mine.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mine = mine.cuda()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, H, generator=g, dtype=torch.double)
+    wy = torch.randn(B, T, H, generator=g, dtype=torch.double) / T ** 0.5
+    xr = x.clone().requires_grad_(True)
+    yr, (hr, cr) = ref(xr)
+    ((yr * wy).sum() + cr.sum()).backward()
+    xm = x.float().cuda().requires_grad_(True)
+    with cluster_budget(budget):
+        ym, (hm, cm) = mine(xm)
+        ((ym * wy.float().cuda()).sum() + cm.sum()).backward()
+    torch.cuda.synchronize()
+    assert _per_step_err(ym, yr) <= STATE_TOL
+    assert rel_err(cm.cpu(), cr) <= STATE_TOL
+    assert rel_l2(xm.grad.cpu(), xr.grad) <= GRAD_TOL
+    for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        assert rel_l2(pm.grad.cpu(), pr.grad) <= GRAD_TOL, name
+
+
+def _bench_model_and_batch():
+    import bench
+    from multimodalreactiongeneration_b200.mr_gen.configs import simple_lstm_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.simple_lstm.simple_lstm import SimpleLSTM
+    torch.manual_seed(0)
+    model = SimpleLSTM(*simple_lstm_cfg(bench.HIDDEN, bench.LAYERS, False, bench.ACOUSTIC, bench.POSE))
+    batch = bench.synthetic_batch(1234, bench.B_PER_GPU, pin=False)
+    return model, batch
+
+
+@pytest.fixture(scope="module")
+def bench_step_truth():
+    """fp64 CPU oracle of ONE training step of the bench model at the bench shape: loss and all gradients."""
+    from oracle import ref_port
+    model, batch = _bench_model_and_batch()
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    loss = ref_port.simple_lstm_training_step(sd, tuple(t.double() for t in batch))
+    loss.backward()
+    return float(loss), {k: v.grad for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("overlap,two_streams", [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")])
+def test_bench_shape_training_step_matches_oracle(bench_step_truth, overlap, two_streams, monkeypatch):
+    """The flat gradient bucket after Trainer.train_step's backward == the oracle's gradients, with the
+    weight-gradient side streams (MRG_WGRAD_OVERLAP) and the two-stream encoders (MRG_TWO_STREAMS) on and off."""
+    from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer
+    monkeypatch.setenv("MRG_WGRAD_OVERLAP", overlap)
+    monkeypatch.setenv("MRG_TWO_STREAMS", two_streams)
+    want_loss, want = bench_step_truth
+    model, batch = _bench_model_and_batch()
+    model = model.cuda()
+    tr = Trainer(model)
+    loss = tr.forward_backward(tuple(t.cuda() for t in batch))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - want_loss) <= 1e-4 * abs(want_loss)
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        e = rel_l2(p.grad.cpu(), want[name])
+        if e > worst[1]:
+            worst = (name, e)
+    assert worst[1] <= GRAD_TOL, worst
+
+
+def _lws_big(B=6, T=300, lead=8, seed=3):
+    from multimodalreactiongeneration_b200.mr_gen.configs import lstm_with_sampling_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.lstm_with_sampling.lstm_with_sample import LSTMwithSample
+    torch.manual_seed(seed)
+    m = LSTMwithSample(*lstm_with_sampling_cfg(max_epochs=10, ratio=1))
+    g = torch.Generator().manual_seed(seed + 1)
+    r = lambda *s: torch.randn(*s, generator=g)
+    ms = r(B, T, 6)
+    tgt = r(B, T, 6)
+    ms[1, T - 40:] = -100.0   # one padded row (collate pads with PADDING_VALUE; Q7 / Q11)
+    tgt[1, T - 40:] = -100.0
+    batch = [r(B, T, 80), r(B, T, 6), ms, r(B, lead, 80), r(B, lead, 6), r(B, lead, 6), tgt]
+    return m, batch
+
+
+@pytest.mark.parametrize("rate", [0.5, 1.0])
+def test_lstm_with_sample_rollout_at_real_sizes_matches_oracle(rate):
+    """H=256 predictor / H=128 sampler (cluster kernels), T=300, per-sample mask, one padded row: prediction, loss
+    and every parameter gradient of the scheduled-sampling training step vs the oracle's step-by-step loop."""
+    from oracle import ref_port
+    m, batch = _lws_big()
+    B, T = batch[1].shape[:2]
+    g = torch.Generator().manual_seed(17)
+    mask = torch.rand(T, B, generator=g) < rate
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    b64 = [t.double() for t in batch]
+    pred_ref = ref_port.lws_rollout(sd, 1, b64, mask)
+    loss_ref = ref_port.masked_loss(pred_ref, b64[6], "huber")
+    loss_ref.backward()
+
+    m = m.cuda()
+    cb = [(t.cuda(), None) for t in batch]
+    pred, target = m.prediction(cb, use_scheduled_sampling=True, sampling_mask=mask)
+    y, tg = m._mask_padding(pred, target)
+    loss = m.lossfun()(y, tg)
+    loss.backward()
+    torch.cuda.synchronize()
+    # free-running steps compound fp32 rounding: the bound is per step of the recursion, checked on the whole window
+    assert rel_err(pred.detach().cpu(), pred_ref) <= (5e-5 if rate < 1.0 else 2e-4)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    for name, p in m.named_parameters():
+        want = sd[name].grad
+        if want is None or float(want.norm()) == 0.0:   # W_hh / forget-gate rows of the stateless predictor (Q2)
+            assert p.grad is None or float(p.grad.abs().max()) <= 1e-12, name
+            continue
+        assert rel_l2(p.grad.cpu(), want) <= GRAD_TOL, name
+
+
+def test_cluster_kernel_index_guard():
+    """(T+1)*B*H*4 must stay below 2^31 in one direction of the cluster kernels: the library refuses the shape
+    instead of wrapping a 32-bit index (mrg_rec_fwd2.cu), and accepts the largest shape below the boundary."""
+    from multimodalreactiongeneration_b200 import _cabi, lstm_layer
+    H = 256
+    k = 1.0 / H ** 0.5
+    w = [torch.empty(4 * H, H, device="cuda").uniform_(-k, k) for _ in range(2)] + \
+        [torch.empty(4 * H, device="cuda").uniform_(-k, k) for _ in range(2)]
+    B = 2048
+    T_bad = (1 << 31) // (B * H * 4) + 1          # (T+1)*B*H*4 >= 2^31
+    x = torch.zeros(T_bad, B, H, device="cuda")
+    with pytest.raises(_cabi.MrgError, match="32-bit index"):
+        with torch.no_grad():
+            lstm_layer(x, w, H, 1)
+    T_ok = (1 << 31) // (B * H * 4) - 2
+    with torch.no_grad():
+        y, h, c = lstm_layer(x[:T_ok], w, H, 1)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(y[-1]).all())

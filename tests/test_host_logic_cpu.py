@@ -20,6 +20,10 @@ def torch_arithmetic(monkeypatch):
     monkeypatch.setattr(B200LSTM, "forward", nn.LSTM.forward)
     monkeypatch.setattr(B200GRU, "forward", nn.GRU.forward)
     monkeypatch.setattr(B200Linear, "forward", nn.Linear.forward)
+    from multimodalreactiongeneration_b200.mr_gen.model.lstm_with_sampling import lstm_with_sample as lws
+    monkeypatch.setattr(lws, "_linear", nn.functional.linear)
+    from multimodalreactiongeneration_b200.attention import B200MultiheadAttention
+    monkeypatch.setattr(B200MultiheadAttention, "forward", nn.MultiheadAttention.forward)
 
 
 NAMES = ["acoustic", "motion_p", "motion_s", "lead_a", "lead_p", "lead_s", "target"]

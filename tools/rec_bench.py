@@ -1,5 +1,5 @@
 """Kernel-level time of the recurrent fwd / BPTT kernels (library CUDA-event hooks) for a few shapes,
-first vs second generation (developer tool, not the bench)."""
+developer tool, not the bench."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -35,7 +35,7 @@ if __name__ == "__main__":
               (64, 300, 128, 2), (1024, 30, 256, 1), (16, 300, 256, 1), (32, 300, 256, 1)]
     for (B, T, H, D) in shapes:
         row = f"B={B:5d} T={T} H={H} D={D}:"
-        for name, fl in (("v2", 0), ("v1", _cabi.F_REC_V1)):
+        for name, fl in (("cluster", 0),):
             try:
                 f, b = run(B, T, H, D, fl)
                 row += f"  {name} fwd {f*1e3:8.1f} us ({f*1e3/T:5.2f}/step) bwd {b*1e3:8.1f} us ({b*1e3/T:5.2f}/step)"
