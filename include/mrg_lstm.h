@@ -10,7 +10,7 @@
  *       mr_gen/model/utils/mixer_block.py:237,251 (LSTMMixer.mixer)
  *   mrg_rollout_forward / _backward      replace the Python time loop of
  *       mr_gen/model/lstm_with_sampling/lstm_with_sample.py:379-408 (head_motion_generation)
- *       + :410-433 (generate_one_step) with one persistent kernel
+ *       + :410-433 (generate_one_step) with one persistent cluster kernel per direction (csrc/mrg_rollout.cu)
  *   mrg_philox_mask                      replaces `torch.rand(length) < epoch/max_epochs`
  *       mr_gen/model/lstm_with_sampling/lstm_with_sample.py:389
  *
@@ -136,6 +136,66 @@ int mrg_residual_layernorm_backward(const float* dout, long long d_s0, long long
                                     float* dsum, long long g_s0, long long g_s1, float* dgamma, float* dbeta,
                                     void* workspace, size_t workspace_bytes, int n0, int n1, int H,
                                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Persistent on-device rollout of lstm_with_sampling — replaces the Python time loop
+ * mr_gen/model/lstm_with_sampling/lstm_with_sample.py:379-408 (head_motion_generation) + :410-433
+ * (generate_one_step) for everything that depends on the previous step (scheduled sampling, step-wise teacher
+ * forcing, free-running generation, streaming with T = 1).  Per step t and batch row b:
+ *     prev   = t == 0 ? gt_prev[0] : (mask[t-1] ? pred[t-1] : gt_prev[t])        (quirks Q5, Q6)
+ *     x_0    = base[t] + W_prev prev
+ *     x_l+1  = LayerNorm_l(cell_l(x_l) + x_l)   cell_l: one nn.LSTM step from zero state (quirk Q2): W_hh and the
+ *                                               forget gate are inert, c = sig(i) tanh(g), h = sig(o) tanh(c)
+ *     pred[t] = W_2 act(W_1 x_L + b_1) + b_2    act = ReLU when relu != 0
+ * base = feature_projection over [sampler output | partner pose] + bias (time-parallel GEMM, the caller's);
+ * W_prev = the last P columns of feature_projection.weight (row stride w_prev_ld).  All tensors time-major.
+ * H in {32, 64, 128, 256}, L in {1, 2}, P <= 32, FB <= 64 and a multiple of H/8: mrg_rollout_supported().
+ * mask: uint8 [T][B] or NULL (never feed back); produce it with mrg_philox_mask for the counter-based RNG. */
+typedef struct mrg_rollout_weights {
+  int H, L, P, FB, relu;
+  float ln_eps;
+  const float* w_prev;        /* [H][P], row stride w_prev_ld */
+  long long w_prev_ld;
+  const float* w_ih[2];       /* [4H][H]  torch gate order i, f, g, o */
+  const float* b_ih[2];       /* [4H] or NULL */
+  const float* b_hh[2];       /* [4H] or NULL */
+  const float* ln_g[2];       /* [H] */
+  const float* ln_b[2];       /* [H] */
+  const float* w1;            /* [FB][H] */
+  const float* b1;            /* [FB] or NULL */
+  const float* w2;            /* [P][FB] */
+  const float* b2;            /* [P] or NULL */
+} mrg_rollout_weights;
+
+/* Written by the forward when non-NULL (training), read by the backward. */
+typedef struct mrg_rollout_reserve {
+  float* xs;     /* [L+1][T][B][H]  x_0 .. x_L */
+  float* gates;  /* [L][T][B][3][H] post-activation i, g, o */
+  float* xhat;   /* [L][T][B][H]    normalised pre-affine LayerNorm values */
+  float* rstd;   /* [L][T][B] */
+  float* fact;   /* [T][B][FB]      FFN hidden after the activation */
+  float* prev;   /* [T][B][P]       the pose that was fed to every step */
+} mrg_rollout_reserve;
+
+/* Outputs of the backward-through-time kernel.  Weight gradients are time-parallel GEMMs / column sums over these:
+ * dW_2 = dy^T fact, db_2 = colsum dy; dW_1 = df^T xs[L], db_1 = colsum df; dW_ih^l = dpre[l]^T xs[l],
+ * db_ih^l = db_hh^l = colsum dpre[l]; d(ln weight) = colsum dln_g[l], d(ln bias) = colsum dln_b[l];
+ * dW_prev = dbase^T prev; d(base) = dbase; d(gt_prev[t]) = dprev[t] where step t was NOT fed back. */
+typedef struct mrg_rollout_grads {
+  float* dy;     /* [T][B][P]   total gradient at pred (loss + fed-back) */
+  float* df;     /* [T][B][FB]  gradient at the FFN hidden pre-activation */
+  float* dpre;   /* [L][T][B][4H] gradient at the gate pre-activations, torch gate order, forget columns zero */
+  float* dbase;  /* [T][B][H] */
+  float* dprev;  /* [T][B][P] */
+  float* dln_g;  /* [L][B][H]   per-row sums over t */
+  float* dln_b;  /* [L][B][H] */
+} mrg_rollout_grads;
+
+int mrg_rollout_supported(int H, int L, int P, int FB);
+int mrg_rollout_forward(const float* base, const float* gt_prev, const uint8_t* mask, const mrg_rollout_weights* w,
+                        float* pred, const mrg_rollout_reserve* reserve, int T, int B, void* stream);
+int mrg_rollout_backward(const float* dpred, const uint8_t* mask, const mrg_rollout_weights* w,
+                         const mrg_rollout_reserve* reserve, const mrg_rollout_grads* g, int T, int B, void* stream);
 
 /* Scheduled-sampling mask: out[t*B+b] = philox4x32_10(ctr=(lo(offset+t), hi(offset+t), shared?0:b, 0),
  * key=(lo(seed), hi(seed)))[0] >> 8 as a 24-bit uniform < prob.  out is a DEVICE uint8 buffer. */

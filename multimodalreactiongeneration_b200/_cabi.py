@@ -19,6 +19,7 @@ EXPORTS = (
     "mrg_gemm_workspace_bytes", "mrg_layernorm_workspace_bytes", "mrg_residual_layernorm_forward",
     "mrg_residual_layernorm_backward", "mrg_adamw_flat", "mrg_debug_set_trace", "mrg_colsum", "mrg_colsum_workspace_bytes",
     "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
+    "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward",
 )
 
 
@@ -30,6 +31,24 @@ class DirWeights(ctypes.Structure):
 class DirGrads(ctypes.Structure):
     _fields_ = [("dw_ih", c_void_p), ("dw_hh", c_void_p), ("db", c_void_p), ("dh0", c_void_p),
                 ("dc0", c_void_p)]
+
+
+class RolloutWeights(ctypes.Structure):
+    _fields_ = [("H", c_int), ("L", c_int), ("P", c_int), ("FB", c_int), ("relu", c_int), ("ln_eps", c_float),
+                ("w_prev", c_void_p), ("w_prev_ld", ctypes.c_longlong),
+                ("w_ih", c_void_p * 2), ("b_ih", c_void_p * 2), ("b_hh", c_void_p * 2),
+                ("ln_g", c_void_p * 2), ("ln_b", c_void_p * 2),
+                ("w1", c_void_p), ("b1", c_void_p), ("w2", c_void_p), ("b2", c_void_p)]
+
+
+class RolloutReserve(ctypes.Structure):
+    _fields_ = [("xs", c_void_p), ("gates", c_void_p), ("xhat", c_void_p), ("rstd", c_void_p), ("fact", c_void_p),
+                ("prev", c_void_p)]
+
+
+class RolloutGrads(ctypes.Structure):
+    _fields_ = [("dy", c_void_p), ("df", c_void_p), ("dpre", c_void_p), ("dbase", c_void_p), ("dprev", c_void_p),
+                ("dln_g", c_void_p), ("dln_b", c_void_p)]
 
 
 class MrgError(RuntimeError):
@@ -107,6 +126,14 @@ def lib() -> ctypes.CDLL:
     L.mrg_gru_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_int, c_int, c_void_p]
     L.mrg_gru_backward.restype = c_int
+    L.mrg_rollout_supported.argtypes = [c_int] * 4
+    L.mrg_rollout_supported.restype = c_int
+    L.mrg_rollout_forward.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(RolloutWeights), c_void_p,
+                                      POINTER(RolloutReserve), c_int, c_int, c_void_p]
+    L.mrg_rollout_forward.restype = c_int
+    L.mrg_rollout_backward.argtypes = [c_void_p, c_void_p, POINTER(RolloutWeights), POINTER(RolloutReserve),
+                                       POINTER(RolloutGrads), c_int, c_int, c_void_p]
+    L.mrg_rollout_backward.restype = c_int
     L.mrg_launch_count.restype = ctypes.c_ulonglong
     L.mrg_profile_enable.argtypes = [c_int]
     L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]

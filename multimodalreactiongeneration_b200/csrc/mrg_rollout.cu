@@ -1,0 +1,893 @@
+// Persistent on-device rollout of lstm_with_sampling (sm_100a): forward and backward-through-time.
+//
+// Replaces the Python time loop of the reference,
+//   mr_gen/model/lstm_with_sampling/lstm_with_sample.py:379-408 (head_motion_generation) and :410-433
+//   (generate_one_step -> forward with T = 1),
+// for the part of a step that depends on the previous step.  What a step of the reference computes (quirks Q2, Q5,
+// Q6 of SURVEY.md Appendix C kept):
+//   prev_t  = t == 0 ? ms[0] : (mask[t-1] ? y_{t-1} : ms[t-1])                      feedback select (:397,:404)
+//   x_0     = W_f [s_t | partner_t | prev_t] + b_f                                   feature_projection (:228)
+//   x_{l+1} = LayerNorm_l(cell_l(x_l) + x_l),   cell_l = nn.LSTM step from ZERO state (Q2):
+//             c = sig(i) * tanh(g), h = sig(o) * tanh(c), (i, f, g, o) = W_ih^l x_l + b_ih^l + b_hh^l
+//             (W_hh and the forget gate are inert: h_0 = c_0 = 0)                    lstm_block.py:101-107, :165-169
+//   y_t     = W_2 relu(W_1 x_L + b_1) + b_2                                          feed_forward (:230)
+// The sampler LSTM (the only carried state) does not depend on the feedback, so it runs once over lead + sequence in
+// the recurrent kernel (mrg_rec_fwd2.cu) and enters here through `base` = W_f[:, :Hs+P] [s | partner] + b_f, a
+// time-parallel GEMM.  This kernel owns everything that is serial in t.
+//
+// Design (same ownership as the recurrent kernels): a thread-block cluster of CL = H/32 CTAs shares a group of batch
+// rows; CTA c owns hidden units [32c, 32c+32) of EVERY predictor layer.  The three live gate rows (i, g, o) of the
+// owned units — 96 x H weights per layer — stay on chip for the whole sequence: the g / o rows in REGISTERS (thread
+// tile = 1 unit x H/16 k-values), the i rows in shared memory (one conflict-free LDS.128 per 4 k-values); the forget
+// rows are never loaded.  Per layer: FFMA2 partial sums -> shared-memory reduction over the k-slices -> gates + cell
+// update + residual (one warp per row, lane = unit) -> the 32 pre-LayerNorm values of every row are written into the
+// shared memory of ALL CTAs of the cluster (st.shared::cluster, 16 bytes per store) -> barrier.cluster -> every CTA
+// normalises the full row redundantly (it needs all H values as the next layer's input).  The bottleneck FFN is
+// split by output unit the same way; the pose, the feedback select and x_0 are computed redundantly per CTA (a few
+// hundred FMAs), so a step has NL + 1 cluster barriers and no other communication.  HBM sees only the per-step
+// inputs (base, ground-truth pose, mask) and, in training, the reserve for the backward.
+//
+// Backward (rollout_bwd_kernel): the same clusters walk t = T-1 .. 0 with the chain dy -> FFN^T -> LN^T -> cell^T ->
+// W_ih^T -> ... -> W_prev^T -> (mask) -> dy_{t-1} (Q6: gradients flow through fed-back poses).  The transposed
+// mat-vec keeps the same weight slice (own gate rows x all k), produces partial dx over the CTA's 96 gate rows and
+// reduce-scatters them to the CTA that owns each k (fixed summation order: deterministic); LayerNorm's two row sums
+// and the P-wide W_prev^T product are small all-reduces over the same shared-memory windows.  Everything that is
+// time-parallel (all weight gradients) is left to the tensor-core GEMMs: the kernel stores d(pre-activations).
+#include <cstdlib>
+
+#include "mrg_common.cuh"
+
+namespace mrg {
+
+constexpr int RO_THREADS = 512;
+constexpr int RO_RCAP = 8;   // batch rows a cluster advances together (one pass over t)
+constexpr int RO_LMAX = 2;   // predictor blocks held on chip
+
+struct RolloutArgs {
+  const float* base;           // [T][B][H]
+  const float* gt_prev;        // [T][B][P]  ground-truth previous pose of every step (one-frame lag, Q5)
+  const unsigned char* mask;   // [T][B]     mask[t] != 0: step t+1 is fed y_t (nullptr = never)
+  const float* w_prev;         // [H][P], row stride w_prev_ld
+  long long w_prev_ld;
+  const float* w_ih[RO_LMAX];  // [4H][H]
+  const float* b_ih[RO_LMAX];  // [4H] or nullptr
+  const float* b_hh[RO_LMAX];
+  const float* ln_g[RO_LMAX];  // [H]
+  const float* ln_b[RO_LMAX];
+  const float *w1, *b1, *w2, *b2;  // [FB][H], [FB], [P][FB], [P]
+  float eps;
+  int T, B, P, FB, relu, train, slices;
+  float* pred;    // [T][B][P]
+  float* xs;      // [NL+1][T][B][H]
+  float* gates;   // [NL][T][B][3][H]   post-activation i, g, o
+  float* xhat;    // [NL][T][B][H]
+  float* rstd;    // [NL][T][B]
+  float* fact;    // [T][B][FB]         FFN hidden, post-activation
+  float* prev;    // [T][B][P]
+  // backward only
+  const float* dpred;  // [T][B][P]
+  float* dy;           // [T][B][P]
+  float* df;           // [T][B][FB]
+  float* dpre;         // [NL][T][B][4H]
+  float* dbase;        // [T][B][H]
+  float* dprev;        // [T][B][P]
+  float* dln_g;        // [NL][B][H]
+  float* dln_b;        // [NL][B][H]
+};
+
+__device__ __forceinline__ void ro_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ro_cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ro_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ro_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float ro_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__host__ __device__ inline int ro_align4(int n) { return (n + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------------------------------
+// shared-memory layouts (offsets in floats, every block 16-byte aligned)
+// ---------------------------------------------------------------------------------------------------------
+struct RoFwdLayout {
+  int wi, part, xfull, vbuf, base, fbuf, fl, w1, w2, wprev, lng, lnb, bias, b1, b2, ysm, gtsm, msm, total;
+};
+__host__ __device__ inline RoFwdLayout ro_fwd_layout(int H, int NL, int P, int FB) {
+  const int CL = H / 32, KSL = H >= 64 ? 16 : 8, PP = P | 1, FBc = FB / CL;
+  RoFwdLayout l;
+  int o = 0;
+  l.wi = o;    o += NL * H * 32;                    // gate-i rows of the owned units: [NL][H/4][32] float4
+  l.part = o;  o += (KSL / 2) * RO_RCAP * 3 * 32;   // partial gate sums [k-slice][row][gate][unit]
+  l.xfull = o; o += RO_RCAP * H;                    // input vector of the current layer, all rows
+  l.vbuf = o;  o += 2 * RO_RCAP * H;                // pre-LayerNorm rows written by all CTAs (two windows)
+  l.base = o;  o += RO_RCAP * H;                    // cp.async landing zone of base[t+1]
+  l.fbuf = o;  o += RO_RCAP * ro_align4(FB);        // FFN hidden written by all CTAs
+  l.fl = o;    o += RO_RCAP * ro_align4(FBc);       // this CTA's part of it
+  l.w1 = o;    o += ro_align4(FBc * H);
+  l.w2 = o;    o += ro_align4(P * FB);
+  l.wprev = o; o += ro_align4(H * PP);
+  l.lng = o;   o += NL * H;
+  l.lnb = o;   o += NL * H;
+  l.bias = o;  o += NL * 3 * 32;
+  l.b1 = o;    o += ro_align4(FBc);
+  l.b2 = o;    o += ro_align4(P);
+  l.ysm = o;   o += ro_align4(RO_RCAP * P);
+  l.gtsm = o;  o += ro_align4(RO_RCAP * P);
+  l.msm = o;   o += RO_RCAP;
+  l.total = o;
+  return l;
+}
+
+// =========================================================================================================
+// forward
+// =========================================================================================================
+template <int H, int NL>
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs a) {
+  constexpr int CL = H / 32;
+  constexpr int KSL = H >= 64 ? 16 : 8;  // k-slices of the mat-vec (one thread covers KT consecutive k)
+  constexpr int KT = H / KSL;
+  constexpr int NCH = KT / 4;
+  constexpr int RC = RO_RCAP;
+  extern __shared__ __align__(16) float sm[];
+  const int P = a.P, FB = a.FB, FBc = FB / CL, PP = P | 1, T = a.T, B = a.B;
+  const RoFwdLayout lay = ro_fwd_layout(H, NL, P, FB);
+  float4* wi_sm = reinterpret_cast<float4*>(sm + lay.wi);
+  float* part = sm + lay.part;
+  float* xfull = sm + lay.xfull;
+  float* vbuf = sm + lay.vbuf;
+  float* basebuf = sm + lay.base;
+  float* fbuf = sm + lay.fbuf;
+  float* fl = sm + lay.fl;
+  float* w1s = sm + lay.w1;
+  float* w2s = sm + lay.w2;
+  float* wprev = sm + lay.wprev;
+  float* lng = sm + lay.lng;
+  float* lnb = sm + lay.lnb;
+  float* bias = sm + lay.bias;
+  float* b1s = sm + lay.b1;
+  float* b2s = sm + lay.b2;
+  float* ysm = sm + lay.ysm;
+  float* gtsm = sm + lay.gtsm;
+  float* msm = sm + lay.msm;
+  const int FBa = ro_align4(FB), FBca = ro_align4(FBc);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / CL;
+  const int j0 = rank * 32;
+  const int base_rows = B / a.slices, rem_rows = B % a.slices;
+  const int crow0 = cid * base_rows + min(cid, rem_rows);
+  const int nrows = base_rows + (cid < rem_rows ? 1 : 0);
+
+  // mat-vec coordinates: lane = (unit within a half, k sub-slice), warp = (k slice pair, unit half)
+  const int u16 = lane & 15, subk = lane >> 4;
+  const int ks = warp % (KSL / 2), uhalf = warp / (KSL / 2);
+  const bool mv = warp < KSL;
+  const int unit = (uhalf & 1) * 16 + u16;
+  const int k0 = (ks * 2 + subk) * KT;
+
+  // ---- weights on chip -------------------------------------------------------------------------------------------
+  float4 wr[NL][2][NCH];  // g and o rows of `unit`, k0 .. k0+KT-1
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (mv) {
+        wr[l][0][c] = __ldg(reinterpret_cast<const float4*>(a.w_ih[l] + (size_t)(2 * H + j0 + unit) * H + k0 + 4 * c));
+        wr[l][1][c] = __ldg(reinterpret_cast<const float4*>(a.w_ih[l] + (size_t)(3 * H + j0 + unit) * H + k0 + 4 * c));
+      } else {
+        wr[l][0][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wr[l][1][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  for (int idx = tid; idx < NL * (H / 4) * 32; idx += RO_THREADS) {
+    const int un = idx & 31, kc = (idx >> 5) % (H / 4), l = idx / ((H / 4) * 32);
+    wi_sm[idx] = __ldg(reinterpret_cast<const float4*>(a.w_ih[l] + (size_t)(j0 + un) * H + kc * 4));
+  }
+  for (int idx = tid; idx < NL * 3 * 32; idx += RO_THREADS) {
+    const int un = idx & 31, g = (idx >> 5) % 3, l = idx / 96;
+    const int row = (g == 0 ? 0 : g == 1 ? 2 * H : 3 * H) + j0 + un;
+    float b = 0.f;
+    if (a.b_ih[l]) b += a.b_ih[l][row];
+    if (a.b_hh[l]) b += a.b_hh[l][row];
+    bias[idx] = b;
+  }
+  for (int idx = tid; idx < NL * H; idx += RO_THREADS) {
+    const int l = idx / H, k = idx % H;
+    lng[idx] = a.ln_g[l][k];
+    lnb[idx] = a.ln_b[l][k];
+  }
+  for (int idx = tid; idx < FBc * H; idx += RO_THREADS) w1s[idx] = a.w1[(size_t)(rank * FBc + idx / H) * H + idx % H];
+  for (int idx = tid; idx < P * FB; idx += RO_THREADS) w2s[idx] = a.w2[idx];
+  for (int idx = tid; idx < H * P; idx += RO_THREADS) wprev[(idx / P) * PP + idx % P] = a.w_prev[(size_t)(idx / P) * a.w_prev_ld + idx % P];
+  for (int idx = tid; idx < FBc; idx += RO_THREADS) b1s[idx] = a.b1 ? a.b1[rank * FBc + idx] : 0.f;
+  for (int idx = tid; idx < P; idx += RO_THREADS) b2s[idx] = a.b2 ? a.b2[idx] : 0.f;
+  __syncthreads();
+  cluster_sync_all();  // every CTA of the cluster is resident before anybody writes into a peer's shared memory
+
+  const int npass = (nrows + RC - 1) / RC;
+  const int rpp = npass > 0 ? (nrows + npass - 1) / npass : 0;
+  const size_t TBH = (size_t)T * B * H;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int prow0 = crow0 + pass * rpp;
+    const int R = min(rpp, crow0 + nrows - prow0);
+    // ---- state of step 0: ground-truth pose, no feedback; base[0] in flight ----
+    if (tid < R * P) gtsm[tid] = a.gt_prev[(size_t)prow0 * P + tid];
+    if (tid < RC) msm[tid] = 0.f;
+    for (int e = tid; e < R * H / 4; e += RO_THREADS)
+      ro_cp_async16(smem_u32(basebuf + 4 * e), a.base + (size_t)prow0 * H + 4 * e);
+    ro_cp_async_commit();
+
+    for (int t = 0; t < T; ++t) {
+      const size_t tb = (size_t)t * B + prow0;  // first row of this pass at step t
+      // ================= phase A: previous pose, x_0 =================
+      ro_cp_async_wait_all();
+      __syncthreads();
+      for (int e = tid; e < R * H; e += RO_THREADS) {
+        const int r = e / H, k = e % H;
+        float acc = basebuf[e];
+        const float* wp = wprev + k * PP;
+        const bool fb = msm[r] != 0.f;
+        for (int p = 0; p < P; ++p) acc = fmaf(wp[p], fb ? ysm[r * P + p] : gtsm[r * P + p], acc);
+        xfull[e] = acc;
+        if (a.train && (k >> 5) == rank) a.xs[(tb + r) * H + k] = acc;
+      }
+      if (a.train && rank == 0 && tid < R * P) {
+        const int r = tid / P;
+        a.prev[tb * P + tid] = msm[r] != 0.f ? ysm[tid] : gtsm[tid];
+      }
+      __syncthreads();
+      float gt_next = 0.f, m_next = 0.f;
+      if (t + 1 < T) {
+        for (int e = tid; e < R * H / 4; e += RO_THREADS)
+          ro_cp_async16(smem_u32(basebuf + 4 * e), a.base + ((size_t)(t + 1) * B + prow0) * H + 4 * e);
+        if (tid < R * P) gt_next = a.gt_prev[((size_t)(t + 1) * B + prow0) * P + tid];
+        if (tid < R && a.mask) m_next = a.mask[tb + tid] ? 1.f : 0.f;
+      }
+      ro_cp_async_commit();
+
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        // ================= phase B: partial gate sums over this thread's k-slice =================
+        if (mv) {
+          for (int rg = 0; rg < R; rg += 4) {
+            float2 acc[3][4];
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) acc[g][r] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              const float4 wi = wi_sm[(l * (H / 4) + (k0 >> 2) + c) * 32 + unit];
+              const float4 wg = wr[l][0][c], wo = wr[l][1][c];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xfull + (rg + r) * H + k0 + 4 * c);
+                const float2 xlo = make_float2(x4.x, x4.y), xhi = make_float2(x4.z, x4.w);
+                ffma2(acc[0][r], make_float2(wi.x, wi.y), xlo);
+                ffma2(acc[0][r], make_float2(wi.z, wi.w), xhi);
+                ffma2(acc[1][r], make_float2(wg.x, wg.y), xlo);
+                ffma2(acc[1][r], make_float2(wg.z, wg.w), xhi);
+                ffma2(acc[2][r], make_float2(wo.x, wo.y), xlo);
+                ffma2(acc[2][r], make_float2(wo.z, wo.w), xhi);
+              }
+            }
+            // the two k sub-slices of a warp meet by shuffle; lanes 0-15 store rows rg, rg+1, lanes 16-31 rg+2, rg+3
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              float s[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                s[r] = acc[g][r].x + acc[g][r].y;
+                s[r] += __shfl_xor_sync(0xffffffffu, s[r], 16);
+              }
+              const int rr = rg + subk * 2;
+              part[((ks * RC + rr) * 3 + g) * 32 + unit] = subk ? s[2] : s[0];
+              part[((ks * RC + rr + 1) * 3 + g) * 32 + unit] = subk ? s[3] : s[1];
+            }
+          }
+        }
+        __syncthreads();
+        // ================= phase C: gates, cell, residual; pre-LayerNorm values to every CTA =================
+        float* vwin = vbuf + (l & 1) * RC * H;
+        if (warp < R) {
+          const int r = warp;
+          float pi = bias[(l * 3 + 0) * 32 + lane], pg = bias[(l * 3 + 1) * 32 + lane], po = bias[(l * 3 + 2) * 32 + lane];
+#pragma unroll
+          for (int s = 0; s < KSL / 2; ++s) {
+            pi += part[((s * RC + r) * 3 + 0) * 32 + lane];
+            pg += part[((s * RC + r) * 3 + 1) * 32 + lane];
+            po += part[((s * RC + r) * 3 + 2) * 32 + lane];
+          }
+          const float gi = fast_sigmoid(pi), gg = fast_tanh(pg), go = fast_sigmoid(po);
+          const float h = go * fast_tanh(gi * gg);
+          const float v = h + xfull[r * H + j0 + lane];
+          if (a.train) {
+            float* gp = a.gates + (((size_t)l * T * B + tb + r) * 3) * H + j0 + lane;
+            gp[0] = gi; gp[H] = gg; gp[2 * H] = go;
+          }
+          float4 hv;
+          hv.x = __shfl_sync(0xffffffffu, v, (lane & ~3));
+          hv.y = __shfl_sync(0xffffffffu, v, (lane & ~3) + 1);
+          hv.z = __shfl_sync(0xffffffffu, v, (lane & ~3) + 2);
+          hv.w = __shfl_sync(0xffffffffu, v, (lane & ~3) + 3);
+          const uint32_t local = smem_u32(vwin + r * H + j0 + (lane & ~3));
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int dst = (lane & 3) + 4 * i;
+            if (dst < CL) st_cluster_v4(map_to_cta(local, (uint32_t)dst), hv);
+          }
+        }
+        cluster_sync_all();
+        // ================= phase D: LayerNorm of the full row (every CTA, redundantly) =================
+        if (warp < R) {
+          const int r = warp;
+          float v[H / 32];
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < H / 32; ++i) { v[i] = vwin[r * H + lane + 32 * i]; s += v[i]; }
+          const float mean = ro_warp_sum(s) * (1.0f / H);
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < H / 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+          const float rs = 1.0f / sqrtf(ro_warp_sum(q) * (1.0f / H) + a.eps);
+#pragma unroll
+          for (int i = 0; i < H / 32; ++i) {
+            const int k = lane + 32 * i;
+            const float xh = (v[i] - mean) * rs;
+            const float out = fmaf(xh, lng[l * H + k], lnb[l * H + k]);
+            xfull[r * H + k] = out;
+            if (a.train && i == rank) {
+              a.xs[(size_t)(l + 1) * TBH + (tb + r) * H + k] = out;
+              a.xhat[(size_t)l * TBH + (tb + r) * H + k] = xh;
+            }
+          }
+          if (a.train && rank == 0 && lane == 0) a.rstd[(size_t)l * T * B + tb + r] = rs;
+        }
+        __syncthreads();
+      }
+
+      // ================= phase E: bottleneck FFN, this CTA's FBc hidden units =================
+      for (int d0 = (tid >> 5) * 2; d0 < R * FBc; d0 += (RO_THREADS / 32) * 2) {  // warp-uniform trip count
+        const int d = d0 + ((tid >> 4) & 1), l16 = tid & 15;
+        const bool ok = d < R * FBc;
+        const int r = ok ? d / FBc : 0, o = ok ? d % FBc : 0;
+        float s = 0.f;
+        for (int k = l16 * 4; k < H; k += 64) {
+          const float4 w4 = *reinterpret_cast<const float4*>(w1s + o * H + k);
+          const float4 x4 = *reinterpret_cast<const float4*>(xfull + r * H + k);
+          s = fmaf(w4.x, x4.x, s); s = fmaf(w4.y, x4.y, s); s = fmaf(w4.z, x4.z, s); s = fmaf(w4.w, x4.w, s);
+        }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (ok && l16 == 0) {
+          s += b1s[o];
+          if (a.relu) s = fmaxf(s, 0.f);
+          fl[r * FBca + o] = s;
+          if (a.train) a.fact[(tb + r) * FB + rank * FBc + o] = s;
+        }
+      }
+      __syncthreads();
+      {
+        const int q4 = FBc / 4;  // float4 pieces per row (FBc % 4 == 0, host-checked)
+        for (int i = tid; i < R * q4 * CL; i += RO_THREADS) {
+          const int dst = i % CL, q = (i / CL) % q4, r = i / (CL * q4);
+          const float4 v4 = *reinterpret_cast<const float4*>(fl + r * FBca + 4 * q);
+          st_cluster_v4(map_to_cta(smem_u32(fbuf + r * FBa + rank * FBc + 4 * q), (uint32_t)dst), v4);
+        }
+      }
+      cluster_sync_all();
+      // ================= phase F: pose (every CTA), state for the next step =================
+      for (int d0 = (tid >> 5) * 8; d0 < R * P; d0 += (RO_THREADS / 32) * 8) {  // warp-uniform trip count
+        const int d = d0 + ((tid >> 2) & 7), sub = tid & 3;
+        const bool ok = d < R * P;
+        const int r = ok ? d / P : 0, p = ok ? d % P : 0;
+        float s = 0.f;
+        for (int o = sub; o < FB; o += 4) s = fmaf(w2s[p * FB + o], fbuf[r * FBa + o], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (ok && sub == 0) {
+          s += b2s[p];
+          ysm[d] = s;
+          if (rank == 0) a.pred[tb * P + d] = s;
+        }
+      }
+      if (tid < R * P) gtsm[tid] = gt_next;   // read in phase A of this step, rewritten for the next one
+      if (tid < R) msm[tid] = m_next;
+      // (phase A of the next step starts with a __syncthreads)
+    }
+    __syncthreads();
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory
+}
+
+// =========================================================================================================
+// backward through time
+// =========================================================================================================
+struct RoBwdLayout {
+  int wi, part, dpre, dv, dx, rbuf, sbuf, pbuf, pl, w1t, w2, wprev, lng, pf, dysm, dfsm, dpn, total;
+};
+__host__ __device__ inline RoBwdLayout ro_bwd_layout(int H, int NL, int P, int FB) {
+  const int CL = H / 32, PP = P | 1, P4 = ro_align4(P);
+  RoBwdLayout l;
+  int o = 0;
+  l.wi = o;    o += NL * H * 32;             // gate-i rows, transposed tiles: [NL][16 j-pairs][H/2 k-pairs] float4
+  l.part = o;  o += 4 * RO_RCAP * H;         // partial dx [j-group][row][k]
+  l.dpre = o;  o += RO_RCAP * 3 * 32;        // d(pre-activations) of the owned units [row][gate][unit]
+  l.dv = o;    o += RO_RCAP * 32;            // residual branch of dx
+  l.dx = o;    o += RO_RCAP * 32;            // gradient at the owned units of the current layer's output
+  l.rbuf = o;  o += CL * RO_RCAP * 32;       // reduce-scatter window [source CTA][row][unit]
+  l.sbuf = o;  o += ro_align4(CL * RO_RCAP * 2);   // LayerNorm row sums [source CTA][row][2]
+  l.pbuf = o;  o += CL * RO_RCAP * P4;       // W_prev^T partial products [source CTA][row][p]
+  l.pl = o;    o += RO_RCAP * P4;            // this CTA's partial products
+  l.w1t = o;   o += FB * 32;                 // W_1[:, owned units] as [FB][32]
+  l.w2 = o;    o += ro_align4(P * FB);
+  l.wprev = o; o += ro_align4(32 * PP);      // W_prev rows of the owned units
+  l.lng = o;   o += NL * 32;
+  l.pf = o;    o += NL * 4 * RO_RCAP * 32;   // cp.async landing zone: xhat, i, g, o of the next step to process
+  l.dysm = o;  o += ro_align4(RO_RCAP * P);
+  l.dfsm = o;  o += RO_RCAP * ro_align4(FB);
+  l.dpn = o;   o += ro_align4(RO_RCAP * P);  // d(prev) of the step processed before (t+1)
+  l.total = o;
+  return l;
+}
+
+template <int H, int NL>
+__global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs a) {
+  constexpr int CL = H / 32;
+  constexpr int RC = RO_RCAP;
+  constexpr int KP = H / 2;           // k-pairs: a mat-vec thread owns columns 2kp, 2kp+1 and 8 of the 32 owned units
+  constexpr int MVT = 4 * KP;         // mat-vec threads (4 unit groups)
+  extern __shared__ __align__(16) float sm[];
+  const int P = a.P, FB = a.FB, PP = P | 1, P4 = ro_align4(P), FBa = ro_align4(FB), T = a.T, B = a.B;
+  const RoBwdLayout lay = ro_bwd_layout(H, NL, P, FB);
+  float4* wi_sm = reinterpret_cast<float4*>(sm + lay.wi);
+  float* part = sm + lay.part;
+  float* dpre_sm = sm + lay.dpre;
+  float* dv_sm = sm + lay.dv;
+  float* dx_sm = sm + lay.dx;
+  float* rbuf = sm + lay.rbuf;
+  float* sbuf = sm + lay.sbuf;
+  float* pbuf = sm + lay.pbuf;
+  float* pl = sm + lay.pl;
+  float* w1t = sm + lay.w1t;
+  float* w2s = sm + lay.w2;
+  float* wprev = sm + lay.wprev;
+  float* lng = sm + lay.lng;
+  float* pf = sm + lay.pf;
+  float* dysm = sm + lay.dysm;
+  float* dfsm = sm + lay.dfsm;
+  float* dpn = sm + lay.dpn;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / CL;
+  const int j0 = rank * 32;
+  const int base_rows = B / a.slices, rem_rows = B % a.slices;
+  const int crow0 = cid * base_rows + min(cid, rem_rows);
+  const int nrows = base_rows + (cid < rem_rows ? 1 : 0);
+  const size_t TBH = (size_t)T * B * H;
+
+  // ---- weights on chip -------------------------------------------------------------------------------------------
+  const bool mv = tid < MVT;
+  const int kp = tid % KP, jg = tid / KP;  // columns 2kp, 2kp+1; owned units 8jg .. 8jg+7
+  // wr[l][gate g/o][jp][c]: (W[j][2kp+c], W[j+1][2kp+c]) with j = 8jg + 2jp
+  float2 wr[NL][2][4][2];
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        float2 r0 = make_float2(0.f, 0.f), r1 = make_float2(0.f, 0.f);
+        if (mv) {
+          const size_t row = (size_t)((g == 0 ? 2 * H : 3 * H) + j0 + 8 * jg + 2 * jp);
+          r0 = __ldg(reinterpret_cast<const float2*>(a.w_ih[l] + row * H + 2 * kp));
+          r1 = __ldg(reinterpret_cast<const float2*>(a.w_ih[l] + (row + 1) * H + 2 * kp));
+        }
+        wr[l][g][jp][0] = make_float2(r0.x, r1.x);
+        wr[l][g][jp][1] = make_float2(r0.y, r1.y);
+      }
+  for (int idx = tid; idx < NL * 16 * KP; idx += RO_THREADS) {
+    const int k2 = idx % KP, jp = (idx / KP) % 16, l = idx / (16 * KP);
+    const float2 r0 = __ldg(reinterpret_cast<const float2*>(a.w_ih[l] + (size_t)(j0 + 2 * jp) * H + 2 * k2));
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(a.w_ih[l] + (size_t)(j0 + 2 * jp + 1) * H + 2 * k2));
+    wi_sm[idx] = make_float4(r0.x, r1.x, r0.y, r1.y);
+  }
+  for (int idx = tid; idx < FB * 32; idx += RO_THREADS) w1t[idx] = a.w1[(size_t)(idx >> 5) * H + j0 + (idx & 31)];
+  for (int idx = tid; idx < P * FB; idx += RO_THREADS) w2s[idx] = a.w2[idx];
+  for (int idx = tid; idx < 32 * P; idx += RO_THREADS) wprev[(idx / P) * PP + idx % P] = a.w_prev[(size_t)(j0 + idx / P) * a.w_prev_ld + idx % P];
+  for (int idx = tid; idx < NL * 32; idx += RO_THREADS) lng[idx] = a.ln_g[idx >> 5][j0 + (idx & 31)];
+  __syncthreads();
+  cluster_sync_all();
+
+  const int npass = (nrows + RC - 1) / RC;
+  const int rpp = npass > 0 ? (nrows + npass - 1) / npass : 0;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int prow0 = crow0 + pass * rpp;
+    const int R = min(rpp, crow0 + nrows - prow0);
+    float dgam[NL], dbet[NL];  // thread (row = warp, unit = lane): sums over t
+#pragma unroll
+    for (int l = 0; l < NL; ++l) dgam[l] = dbet[l] = 0.f;
+    if (tid < RC * P) dpn[tid] = 0.f;
+    for (int i = tid; i < RC * P4; i += RO_THREADS) pl[i] = 0.f;   // the padding columns travel with the rest
+    // reserve of step T-1 for thread (row, unit): xhat, i, g, o of every layer
+    if (warp < R && T > 0) {
+      const size_t tb = (size_t)(T - 1) * B + prow0 + warp;
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        ro_cp_async4(smem_u32(pf + ((l * 4 + 0) * RC + warp) * 32 + lane), a.xhat + (size_t)l * TBH + tb * H + j0 + lane);
+        const float* gp = a.gates + (((size_t)l * T * B + tb) * 3) * H + j0 + lane;
+        ro_cp_async4(smem_u32(pf + ((l * 4 + 1) * RC + warp) * 32 + lane), gp);
+        ro_cp_async4(smem_u32(pf + ((l * 4 + 2) * RC + warp) * 32 + lane), gp + H);
+        ro_cp_async4(smem_u32(pf + ((l * 4 + 3) * RC + warp) * 32 + lane), gp + 2 * H);
+      }
+    }
+    ro_cp_async_commit();
+    float dp_next = 0.f, m_cur = 0.f, f_cur = 0.f, rs_next[NL];
+    if (T > 0) {
+      if (tid < R * P) dp_next = a.dpred[((size_t)(T - 1) * B + prow0) * P + tid];
+      if (tid < R * FB) f_cur = a.fact[((size_t)(T - 1) * B + prow0 + tid / FB) * FB + tid % FB];
+#pragma unroll
+      for (int l = 0; l < NL; ++l) rs_next[l] = warp < R ? a.rstd[(size_t)l * T * B + (size_t)(T - 1) * B + prow0 + warp] : 0.f;
+    }
+    __syncthreads();
+
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t tb = (size_t)t * B + prow0;
+      // ================= phase 0: total gradient at the pose =================
+      // mask[t] says whether y_t was fed to step t+1 (whose d(prev) sits in dpn)
+      if (tid < R * P) {
+        const float dyv = dp_next + (m_cur != 0.f ? dpn[tid] : 0.f);
+        dysm[tid] = dyv;
+        if (rank == 0) a.dy[tb * P + tid] = dyv;
+      }
+      const float fval = f_cur;
+      float rs[NL];
+#pragma unroll
+      for (int l = 0; l < NL; ++l) rs[l] = rs_next[l];
+      // loads for step t-1, consumed one iteration later
+      if (t > 0) {
+        if (tid < R * P) dp_next = a.dpred[((size_t)(t - 1) * B + prow0) * P + tid];
+        if (tid < R * P && a.mask) m_cur = a.mask[(size_t)(t - 1) * B + prow0 + tid / P] ? 1.f : 0.f;
+        if (tid < R * FB) f_cur = a.fact[((size_t)(t - 1) * B + prow0 + tid / FB) * FB + tid % FB];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) rs_next[l] = warp < R ? a.rstd[(size_t)l * T * B + (size_t)(t - 1) * B + prow0 + warp] : 0.f;
+      }
+      __syncthreads();
+      // ================= phase 1: FFN hidden gradient (every CTA, all FB units) =================
+      if (tid < R * FB) {
+        const int r = tid / FB, o = tid % FB;
+        float s = 0.f;
+        for (int p = 0; p < P; ++p) s = fmaf(w2s[p * FB + o], dysm[r * P + p], s);
+        if (a.relu && !(fval > 0.f)) s = 0.f;
+        dfsm[r * FBa + o] = s;
+        if (rank == 0) a.df[tb * FB + tid] = s;
+      }
+      __syncthreads();
+      // ================= phase 2: gradient at x_L, owned units =================
+      for (int d0 = (tid >> 5) * 8; d0 < R * 32; d0 += (RO_THREADS / 32) * 8) {  // warp-uniform trip count
+        const int d = d0 + ((tid >> 2) & 7), sub = tid & 3;
+        const int r = d >> 5, k = d & 31;
+        float s = 0.f;
+        for (int o = sub; o < FB; o += 4) s = fmaf(w1t[o * 32 + k], dfsm[r * FBa + o], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (sub == 0) dx_sm[d] = s;
+      }
+      ro_cp_async_wait_all();  // reserve of this step (issued one step ago by the same thread)
+      __syncthreads();
+
+#pragma unroll
+      for (int l = NL - 1; l >= 0; --l) {
+        // ================= phase 3: LayerNorm^T row sums, exchanged between the CTAs =================
+        float gdx = 0.f, xh = 0.f, gi = 0.f, gg = 0.f, go = 0.f;
+        if (warp < R) {
+          const int r = warp;
+          const float dxo = dx_sm[r * 32 + lane];
+          xh = pf[((l * 4 + 0) * RC + r) * 32 + lane];
+          gi = pf[((l * 4 + 1) * RC + r) * 32 + lane];
+          gg = pf[((l * 4 + 2) * RC + r) * 32 + lane];
+          go = pf[((l * 4 + 3) * RC + r) * 32 + lane];
+          gdx = dxo * lng[l * 32 + lane];
+          dgam[l] = fmaf(dxo, xh, dgam[l]);
+          dbet[l] += dxo;
+          const float s1 = ro_warp_sum(gdx), s2 = ro_warp_sum(gdx * xh);
+          if (lane < CL) {
+            const uint32_t addr = map_to_cta(smem_u32(sbuf + (rank * RC + r) * 2), (uint32_t)lane);
+            st_cluster_f32(addr, s1);
+            st_cluster_f32(addr + 4, s2);
+          }
+        }
+        cluster_sync_all();
+        // ================= phase 4: LayerNorm^T, cell^T (owned units) =================
+        if (warp < R) {
+          const int r = warp;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < CL; ++c) { s1 += sbuf[(c * RC + r) * 2]; s2 += sbuf[(c * RC + r) * 2 + 1]; }
+          const float dv = rs[l] * (gdx - s1 * (1.0f / H) - xh * s2 * (1.0f / H));
+          const float c = gi * gg, tc = fast_tanh(c);
+          const float d_o = dv * tc * go * (1.f - go);
+          const float dc = dv * go * (1.f - tc * tc);
+          const float d_i = dc * gg * gi * (1.f - gi);
+          const float d_g = dc * gi * (1.f - gg * gg);
+          dv_sm[r * 32 + lane] = dv;
+          dpre_sm[(r * 3 + 0) * 32 + lane] = d_i;
+          dpre_sm[(r * 3 + 1) * 32 + lane] = d_g;
+          dpre_sm[(r * 3 + 2) * 32 + lane] = d_o;
+          float* dp = a.dpre + ((size_t)l * T * B + tb + r) * 4 * H + j0 + lane;   // torch gate order i, f, g, o
+          dp[0] = d_i; dp[H] = 0.f; dp[2 * H] = d_g; dp[3 * H] = d_o;
+        }
+        __syncthreads();
+        // ================= phase 5: W_ih^T over the owned gate rows -> partial dx for every k =================
+        if (mv) {
+          for (int rg = 0; rg < R; rg += 4) {
+            float2 acc[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+              const float4 wi = wi_sm[(l * 16 + jg * 4 + jp) * KP + kp];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const float* dr = dpre_sm + (rg + r) * 96 + 8 * jg + 2 * jp;
+                const float2 di = *reinterpret_cast<const float2*>(dr);
+                const float2 dg = *reinterpret_cast<const float2*>(dr + 32);
+                const float2 dd = *reinterpret_cast<const float2*>(dr + 64);
+                ffma2(acc[r][0], make_float2(wi.x, wi.y), di);
+                ffma2(acc[r][1], make_float2(wi.z, wi.w), di);
+                ffma2(acc[r][0], wr[l][0][jp][0], dg);
+                ffma2(acc[r][1], wr[l][0][jp][1], dg);
+                ffma2(acc[r][0], wr[l][1][jp][0], dd);
+                ffma2(acc[r][1], wr[l][1][jp][1], dd);
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              *reinterpret_cast<float2*>(part + (jg * RC + rg + r) * H + 2 * kp) =
+                  make_float2(acc[r][0].x + acc[r][0].y, acc[r][1].x + acc[r][1].y);
+          }
+        }
+        __syncthreads();
+        // sum the 4 unit groups and hand every k to the CTA that owns it (window slot = this CTA's rank)
+        for (int i = tid; i < R * (H / 4); i += RO_THREADS) {
+          const int r = i / (H / 4), k4 = (i % (H / 4)) * 4;
+          float4 s = *reinterpret_cast<const float4*>(part + (0 * RC + r) * H + k4);
+#pragma unroll
+          for (int g = 1; g < 4; ++g) {
+            const float4 q = *reinterpret_cast<const float4*>(part + (g * RC + r) * H + k4);
+            s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+          }
+          const uint32_t addr = map_to_cta(smem_u32(rbuf + (rank * RC + r) * 32 + (k4 & 31)), (uint32_t)(k4 >> 5));
+          st_cluster_v4(addr, s);
+        }
+        cluster_sync_all();
+        // ================= phase 6: gradient at the layer's input, owned units =================
+        if (warp < R) {
+          const int r = warp;
+          float s = dv_sm[r * 32 + lane];
+#pragma unroll
+          for (int c = 0; c < CL; ++c) s += rbuf[(c * RC + r) * 32 + lane];
+          dx_sm[r * 32 + lane] = s;
+          if (l == 0) a.dbase[(tb + r) * H + j0 + lane] = s;
+        }
+        // dx_sm is read next by the same thread (phase 3 of layer l-1) or after the barrier below (phase 7)
+      }
+      __syncthreads();
+      // reserve of step t-1 into the landing zone just consumed
+      if (t > 0 && warp < R) {
+        const size_t tbn = (size_t)(t - 1) * B + prow0 + warp;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          ro_cp_async4(smem_u32(pf + ((l * 4 + 0) * RC + warp) * 32 + lane), a.xhat + (size_t)l * TBH + tbn * H + j0 + lane);
+          const float* gp = a.gates + (((size_t)l * T * B + tbn) * 3) * H + j0 + lane;
+          ro_cp_async4(smem_u32(pf + ((l * 4 + 1) * RC + warp) * 32 + lane), gp);
+          ro_cp_async4(smem_u32(pf + ((l * 4 + 2) * RC + warp) * 32 + lane), gp + H);
+          ro_cp_async4(smem_u32(pf + ((l * 4 + 3) * RC + warp) * 32 + lane), gp + 2 * H);
+        }
+      }
+      ro_cp_async_commit();
+      // ================= phase 7: W_prev^T over the owned units, all-reduced =================
+      for (int d0 = (tid >> 5) * 4; d0 < R * P; d0 += (RO_THREADS / 32) * 4) {  // warp-uniform trip count
+        const int d = d0 + ((tid >> 3) & 3), sub = tid & 7;
+        const bool ok = d < R * P;
+        const int r = ok ? d / P : 0, p = ok ? d % P : 0;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s = fmaf(wprev[(sub + 8 * i) * PP + p], dx_sm[r * 32 + sub + 8 * i], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (ok && sub == 0) pl[r * P4 + p] = s;
+      }
+      __syncthreads();
+      for (int i = tid; i < R * (P4 / 4) * CL; i += RO_THREADS) {
+        const int dst = i % CL, q = (i / CL) % (P4 / 4), r = i / (CL * (P4 / 4));
+        const float4 v4 = *reinterpret_cast<const float4*>(pl + r * P4 + 4 * q);
+        st_cluster_v4(map_to_cta(smem_u32(pbuf + (rank * RC + r) * P4 + 4 * q), (uint32_t)dst), v4);
+      }
+      cluster_sync_all();
+      if (tid < R * P) {
+        const int r = tid / P, p = tid % P;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) s += pbuf[(c * RC + r) * P4 + p];
+        dpn[tid] = s;
+        if (rank == 0) a.dprev[tb * P + tid] = s;
+      }
+      // (phase 0 of the next iteration reads dpn after its own __syncthreads ... see below)
+      __syncthreads();
+    }
+    if (warp < R) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        a.dln_g[((size_t)l * B + prow0 + warp) * H + j0 + lane] = dgam[l];
+        a.dln_b[((size_t)l * B + prow0 + warp) * H + j0 + lane] = dbet[l];
+      }
+    }
+    __syncthreads();
+  }
+  cluster_sync_all();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+template <typename K>
+static int ro_max_clusters(K kernel, int CL, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CL * 64));
+  cfg.blockDim = dim3(RO_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+template <int H, int NL>
+static int ro_launch(RolloutArgs a, bool backward, cudaStream_t stream) {
+  constexpr int CL = H / 32;
+  const size_t smem = sizeof(float) * (size_t)(backward ? ro_bwd_layout(H, NL, a.P, a.FB).total
+                                                        : ro_fwd_layout(H, NL, a.P, a.FB).total);
+  if (smem > 227 * 1024) {
+    set_error("mrg_rollout: %zu bytes of shared memory needed (P = %d, bottleneck = %d too large)", smem, a.P, a.FB);
+    return MRG_E_UNSUPPORTED;
+  }
+  auto kernel = backward ? rollout_bwd_kernel<H, NL> : rollout_fwd_kernel<H, NL>;
+  static size_t attr_smem[2] = {0, 0};
+  static int maxc[2] = {0, 0};
+  if (smem > attr_smem[backward]) {
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[backward] = smem;
+    maxc[backward] = ro_max_clusters(kernel, CL, smem);
+  }
+  int clusters = maxc[backward] > 0 ? maxc[backward] : 120 / CL;
+  static int forced = -1;  // MRG_ROLLOUT_CLUSTERS: tuning / tests of the multi-pass path
+  if (forced < 0) {
+    const char* e = getenv("MRG_ROLLOUT_CLUSTERS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) clusters = forced;
+  if (clusters > a.B) clusters = a.B;
+  a.slices = clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(RO_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope prof(backward ? PROF_REC_BWD : PROF_REC_FWD, stream);
+  count_launch();
+  MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, a));
+  return 0;
+}
+
+template <int H>
+static int ro_dispatch_layers(const RolloutArgs& a, int L, bool backward, cudaStream_t stream) {
+  return L == 1 ? ro_launch<H, 1>(a, backward, stream) : ro_launch<H, 2>(a, backward, stream);
+}
+
+static int ro_dispatch(const RolloutArgs& a, int H, int L, bool backward, cudaStream_t stream) {
+  switch (H) {
+    case 32: return ro_dispatch_layers<32>(a, L, backward, stream);
+    case 64: return ro_dispatch_layers<64>(a, L, backward, stream);
+    case 128: return ro_dispatch_layers<128>(a, L, backward, stream);
+    case 256: return ro_dispatch_layers<256>(a, L, backward, stream);
+  }
+  set_error("mrg_rollout: hidden size %d not built (32, 64, 128, 256 are)", H);
+  return MRG_E_UNSUPPORTED;
+}
+
+static bool ro_shape_ok(int H, int L, int P, int FB) {
+  if (!(H == 32 || H == 64 || H == 128 || H == 256) || L < 1 || L > RO_LMAX) return false;
+  const int CL = H / 32;
+  if (P < 1 || P > 32 || FB < 4 * CL || FB > 64 || FB % (4 * CL) != 0) return false;
+  return true;
+}
+
+static int ro_fill(RolloutArgs& a, const mrg_rollout_weights* w, const mrg_rollout_reserve* rs, int T, int B) {
+  a.w_prev = w->w_prev; a.w_prev_ld = w->w_prev_ld;
+  for (int l = 0; l < w->L; ++l) {
+    a.w_ih[l] = w->w_ih[l]; a.b_ih[l] = w->b_ih[l]; a.b_hh[l] = w->b_hh[l];
+    a.ln_g[l] = w->ln_g[l]; a.ln_b[l] = w->ln_b[l];
+  }
+  a.w1 = w->w1; a.b1 = w->b1; a.w2 = w->w2; a.b2 = w->b2;
+  a.eps = w->ln_eps; a.T = T; a.B = B; a.P = w->P; a.FB = w->FB; a.relu = w->relu;
+  if (rs) {
+    a.xs = rs->xs; a.gates = rs->gates; a.xhat = rs->xhat; a.rstd = rs->rstd; a.fact = rs->fact; a.prev = rs->prev;
+  }
+  return 0;
+}
+
+static int ro_check(const char* who, const mrg_rollout_weights* w, int T, int B) {
+  MRG_REQUIRE(w != nullptr && T >= 0 && B > 0, "%s: bad arguments", who);
+  MRG_REQUIRE(ro_shape_ok(w->H, w->L, w->P, w->FB),
+              "%s: shape not built (H = %d in {32,64,128,256}, L = %d <= 2, P = %d <= 32, bottleneck = %d: multiple of "
+              "H/8, <= 64)", who, w->H, w->L, w->P, w->FB);
+  MRG_REQUIRE(w->w_prev && w->w1 && w->w2 && w->w_prev_ld >= w->P, "%s: null weights", who);
+  for (int l = 0; l < w->L; ++l)
+    MRG_REQUIRE(w->w_ih[l] && w->ln_g[l] && w->ln_b[l] && (((uintptr_t)w->w_ih[l]) & 15) == 0,
+                "%s: layer %d: null or unaligned weights", who, l);
+  MRG_REQUIRE((long long)T * B * w->H < (1LL << 31), "%s: T*B*H exceeds the 32-bit index range", who);
+  return 0;
+}
+
+}  // namespace mrg
+
+using namespace mrg;
+
+extern "C" int mrg_rollout_supported(int H, int L, int P, int FB) { return ro_shape_ok(H, L, P, FB) ? 1 : 0; }
+
+extern "C" int mrg_rollout_forward(const float* base, const float* gt_prev, const uint8_t* mask,
+                                   const mrg_rollout_weights* w, float* pred, const mrg_rollout_reserve* reserve,
+                                   int T, int B, void* stream) {
+  if (int e = ro_check("mrg_rollout_forward", w, T, B)) return e;
+  MRG_REQUIRE(base && gt_prev && pred && (((uintptr_t)base) & 15) == 0, "mrg_rollout_forward: null / unaligned tensors");
+  if (T == 0) return 0;
+  RolloutArgs a = {};
+  ro_fill(a, w, reserve, T, B);
+  a.base = base; a.gt_prev = gt_prev; a.mask = mask; a.pred = pred;
+  a.train = reserve ? 1 : 0;
+  if (reserve)
+    MRG_REQUIRE(reserve->xs && reserve->gates && reserve->xhat && reserve->rstd && reserve->fact && reserve->prev,
+                "mrg_rollout_forward: incomplete reserve");
+  return ro_dispatch(a, w->H, w->L, false, (cudaStream_t)stream);
+}
+
+extern "C" int mrg_rollout_backward(const float* dpred, const uint8_t* mask, const mrg_rollout_weights* w,
+                                    const mrg_rollout_reserve* reserve, const mrg_rollout_grads* g, int T, int B,
+                                    void* stream) {
+  if (int e = ro_check("mrg_rollout_backward", w, T, B)) return e;
+  MRG_REQUIRE(dpred && reserve && g, "mrg_rollout_backward: null tensors");
+  MRG_REQUIRE(reserve->gates && reserve->xhat && reserve->rstd && reserve->fact, "mrg_rollout_backward: incomplete reserve");
+  MRG_REQUIRE(g->dy && g->df && g->dpre && g->dbase && g->dprev && g->dln_g && g->dln_b,
+              "mrg_rollout_backward: incomplete gradient set");
+  if (T == 0) return 0;
+  RolloutArgs a = {};
+  ro_fill(a, w, reserve, T, B);
+  a.mask = mask; a.dpred = dpred;
+  a.dy = g->dy; a.df = g->df; a.dpre = g->dpre; a.dbase = g->dbase; a.dprev = g->dprev;
+  a.dln_g = g->dln_g; a.dln_b = g->dln_b;
+  return ro_dispatch(a, w->H, w->L, true, (cudaStream_t)stream);
+}

@@ -11,7 +11,16 @@ Q6 gradients flow through fed-back predictions, Q7 loss averaged over padded pos
 Extensions (BASELINE.json north_star): ``sampling_mask`` may be supplied ([T] or [T, B] bool) — e.g.
 from the counter-based Philox generator (``philox_sampling_mask``), bit-exact for a given seed.
 
-Device-resident rollout (``rollout="wavefront"``, the default on CUDA).  Because of Q2 the predictor
+Rollout schedules (``model.rollout``):
+``"kernel"`` (default): the whole T loop of the predictor — feedback select, feature projection of the fed-back pose,
+the zero-state LSTM blocks + LayerNorm, the bottleneck FFN — runs inside ONE persistent cluster kernel per direction
+(``multimodalreactiongeneration_b200.rollout``, C-ABI ``mrg_rollout_forward/backward``); the sampler LSTM, which does not
+depend on the feedback, runs once over lead + sequence in the recurrent kernel and enters as a time-parallel GEMM.  No
+host read, no per-step launch, the launch count does not depend on T or on the sampling rate.  Configurations the
+kernel is not built for (mixing Linear inside the blocks, no LayerNorm, more than 2 blocks, ...) take the wavefront
+schedule below, which runs on the same library kernels.
+
+``"wavefront"``: device-resident re-scheduling with the per-layer kernels.  Because of Q2 the predictor
 restarts from zero state at every step, so step t depends on step t-1 ONLY through the fed-back 6..18-d
 pose, and only where the mask says "feed the prediction back".  The rollout is therefore re-scheduled
 without changing any arithmetic: the sampler LSTM runs ONCE over lead+sequence (identical recurrence to the
@@ -26,6 +35,7 @@ import torch
 from torch import nn
 
 from ....linear import B200Linear, _LinearFn
+from .... import rollout as _rollout
 
 from ....import _cabi
 from ...utils.lightning_shim import LightningModule
@@ -102,8 +112,9 @@ class LSTMwithSample(LightningModule):
         self.sampling_seed: Optional[int] = model.get("sampling_seed", None)
         self.sampling_offset = 0
         self.sampling_per_sample = model.get("sampling_per_sample", True)
-        # "wavefront": device-resident re-scheduled rollout; "stepwise": the reference's Python time loop
-        self.rollout = model.get("rollout", "wavefront")
+        # "kernel": one persistent kernel per direction; "wavefront": re-scheduled rollout on the per-layer kernels;
+        # "stepwise": the reference's Python time loop (cross-check)
+        self.rollout = model.get("rollout", "kernel")
 
     # ------------------------------------------------------------------------------------------
     def forward(self, acoustic_partner: InputTypes, motion_partner: InputTypes, motion_self: InputTypes,
@@ -189,7 +200,9 @@ class LSTMwithSample(LightningModule):
     # ------------------------------------------------------------------------------------------
     def prediction(self, batch: List[InputTypes], use_scheduled_sampling: bool = False,
                    full_generation: bool = False, sampling_mask: Optional[torch.Tensor] = None):
-        if self.rollout == "wavefront":
+        if self.rollout == "kernel" and self._kernel_rollout_layers() is not None:
+            return self._prediction_kernel(batch, use_scheduled_sampling, full_generation, sampling_mask)
+        if self.rollout in ("kernel", "wavefront"):
             return self._prediction_wavefront(batch, use_scheduled_sampling, full_generation, sampling_mask)
         formed, dummy, length = self.batch_forming(batch)
         target = batch[-1][0].to(self.device)
@@ -205,6 +218,65 @@ class LSTMwithSample(LightningModule):
             else:
                 sampling_mask = torch.full((length,), bool(full_generation), dtype=torch.bool)
         return sampling_mask
+
+    def _kernel_rollout_layers(self):
+        """[(w_ih, b_ih, b_hh, ln_weight, ln_bias)] of the predictor blocks when the persistent rollout kernel is
+        built for this configuration (residual + LayerNorm blocks of one uni-directional LSTM layer, no mixing
+        Linear, no block FFN, no active dropout), else None."""
+        from ..utils.residual_connection import ResidualConnection
+        layers = []
+        for block in self.layerd_lstm.lstm_layered:
+            rc = block.lstm_module
+            if block.use_feed_forward or not isinstance(rc, ResidualConnection) or rc.layer_norm is None:
+                return None
+            ln, core = rc.layer_norm, rc.module
+            lstm = core.lstm_module
+            if (core.mixer is not None or lstm.num_layers != 1 or lstm.bidirectional or not ln.elementwise_affine
+                    or ln.bias is None or lstm.input_size != lstm.hidden_size
+                    or (self.training and (rc.dropout.p > 0 or lstm.dropout > 0))):
+                return None
+            layers.append((lstm.weight_ih_l0, lstm.bias_ih_l0 if lstm.bias else None,
+                           lstm.bias_hh_l0 if lstm.bias else None, ln.weight, ln.bias))
+        ff = self.feed_forward
+        H, P, FB = self.feature_projection.out_features, ff.mapping.out_features, ff.input.out_features
+        if not layers or len({float(b.lstm_module.layer_norm.eps) for b in self.layerd_lstm.lstm_layered}) != 1:
+            return None
+        if not self.feature_projection.weight.is_cuda or not _rollout.supported(H, len(layers), P, FB):
+            return None
+        return layers
+
+    def _prediction_kernel(self, batch, use_scheduled_sampling, full_generation, sampling_mask):
+        dev = self.device
+        (a, _), (mp, _), (ms, _), (la, _) = batch[:4]
+        a, mp, ms, la = a.to(dev), mp.to(dev), ms.to(dev), la.to(dev)
+        target = batch[-1][0].to(dev)
+        B, T, P = mp.shape
+        if T == 0:
+            return ms.new_zeros((B, 0, P)), target
+        if sampling_mask is None and not use_scheduled_sampling:
+            # step-wise teacher forcing (never feed back) / free running (always): no draw, nothing from the host
+            mask = torch.ones((T, B), dtype=torch.uint8, device=dev) if full_generation else None
+        else:
+            mask = self._resolve_mask(T, B, use_scheduled_sampling, full_generation, sampling_mask).to(dev)
+            if mask.dim() == 1:
+                mask = mask.view(T, 1).expand(T, B)
+            mask = mask.to(torch.uint8).contiguous()
+        layers = self._kernel_rollout_layers()
+        # time-parallel part: sampler recurrence over lead + sequence (the carried state), projections
+        lead_frames = la.shape[1] // self.ratio
+        sampled, _ = self.sampling_lstm(self.acoustic_projection(torch.cat([la, a], dim=1)), None)
+        sampled = sampled[:, lead_frames:]                                          # [B, T, Hs]
+        Hs = sampled.shape[-1]
+        W, bias = self.feature_projection.weight, self.feature_projection.bias
+        feats = torch.cat([sampled, mp], dim=-1).transpose(0, 1).contiguous()       # [T, B, Hs + P]
+        base = _linear(feats, W[:, :Hs + P], bias)                                   # [T, B, Hd]
+        # ground-truth previous frame with the reference's one-frame lag (Q5): ms[0], ms[0], ms[1], ...
+        gt_prev = torch.cat([ms[:, :1], ms[:, :-1]], dim=1).transpose(0, 1).contiguous()
+        ff = self.feed_forward
+        eps = self.layerd_lstm.lstm_layered[0].lstm_module.layer_norm.eps
+        pred = _rollout.rollout(base, gt_prev, mask, W[:, Hs + P:], layers, ff.input.weight, ff.input.bias,
+                                ff.mapping.weight, ff.mapping.bias, relu=hasattr(ff, "relu"), eps=eps)
+        return pred.transpose(0, 1).contiguous(), target
 
     def _prediction_wavefront(self, batch, use_scheduled_sampling, full_generation, sampling_mask):
         dev = self.device
