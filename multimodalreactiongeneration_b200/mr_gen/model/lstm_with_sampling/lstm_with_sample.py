@@ -220,7 +220,7 @@ class LSTMwithSample(LightningModule):
         return sampling_mask
 
     def _kernel_rollout_layers(self):
-        """[(w_ih, b_ih, b_hh, ln_weight, ln_bias)] of the predictor blocks when the persistent rollout kernel is
+        """[(w_ih, w_hh, b_ih, b_hh, ln_weight, ln_bias)] of the predictor blocks when the persistent rollout kernel is
         built for this configuration (residual + LayerNorm blocks of one uni-directional LSTM layer, no mixing
         Linear, no block FFN, no active dropout), else None."""
         from ..utils.residual_connection import ResidualConnection
@@ -235,7 +235,7 @@ class LSTMwithSample(LightningModule):
                     or ln.bias is None or lstm.input_size != lstm.hidden_size
                     or (self.training and (rc.dropout.p > 0 or lstm.dropout > 0))):
                 return None
-            layers.append((lstm.weight_ih_l0, lstm.bias_ih_l0 if lstm.bias else None,
+            layers.append((lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0 if lstm.bias else None,
                            lstm.bias_hh_l0 if lstm.bias else None, ln.weight, ln.bias))
         ff = self.feed_forward
         H, P, FB = self.feature_projection.out_features, ff.mapping.out_features, ff.input.out_features

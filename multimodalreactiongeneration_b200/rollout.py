@@ -27,7 +27,7 @@ def _weights_struct(H, L, P, FB, relu, eps, w_prev, layers, w1, b1, w2, b2):
     w = _cabi.RolloutWeights()
     w.H, w.L, w.P, w.FB, w.relu, w.ln_eps = H, L, P, FB, int(relu), float(eps)
     w.w_prev, w.w_prev_ld = w_prev.data_ptr(), w_prev.stride(0)
-    for l, (w_ih, b_ih, b_hh, g, b) in enumerate(layers):
+    for l, (w_ih, _w_hh, b_ih, b_hh, g, b) in enumerate(layers):
         w.w_ih[l], w.b_ih[l], w.b_hh[l] = w_ih.data_ptr(), _cabi.ptr(b_ih), _cabi.ptr(b_hh)
         w.ln_g[l], w.ln_b[l] = g.data_ptr(), b.data_ptr()
     w.w1, w.b1, w.w2, w.b2 = w1.data_ptr(), _cabi.ptr(b1), w2.data_ptr(), _cabi.ptr(b2)
@@ -53,14 +53,15 @@ def _into_or_return(grad: torch.Tensor, param: torch.Tensor) -> Optional[torch.T
 class _RolloutFn(torch.autograd.Function):
     """pred[T,B,P] = rollout(base[T,B,H], gt_prev[T,B,P], mask[T,B] u8 | None; weights).  Inputs of the node:
     base, gt_prev, w_prev (a view of feature_projection.weight[:, -P:]), w1, b1, w2, b2, then per layer
-    (w_ih, b_ih, b_hh, ln_weight, ln_bias)."""
+    (w_ih, w_hh, b_ih, b_hh, ln_weight, ln_bias).  ``w_hh`` takes no part in the arithmetic (zero state, quirk Q2) but is
+    a node input so that it receives the exact-zero gradient the reference's graph gives it."""
 
     @staticmethod
     def forward(ctx, base, gt_prev, mask, relu, eps, w_prev, w1, b1, w2, b2, *layer_params):
         if not base.is_cuda:
             raise RuntimeError("rollout has no CPU path: tensors must live on a B200 (sm_100a) device")
-        L = len(layer_params) // 5
-        layers = [layer_params[5 * l:5 * l + 5] for l in range(L)]
+        L = len(layer_params) // 6
+        layers = [layer_params[6 * l:6 * l + 6] for l in range(L)]
         T, B, H = base.shape
         P, FB = w2.shape
         dev = base.device
@@ -155,21 +156,24 @@ class _RolloutFn(torch.autograd.Function):
         d_b2 = bgrad(dy2, b2p) if (b2p is not None and ni[9]) else None
         out: List[Optional[torch.Tensor]] = []
         for l in range(L):
-            w_ih, b_ih, b_hh, ln_g, ln_b = layers[l]
+            w_ih, w_hh, b_ih, b_hh, ln_g, ln_b = layers[l]
             dpre2 = g["dpre"][l].view(M, 4 * H)
-            k = 10 + 5 * l
+            k = 10 + 6 * l
             d_wih = wgrad(dpre2, keep["xs"][l].view(M, H), w_ih) if ni[k] else None
+            d_whh = None   # h_0 = 0 at every step: exactly zero (the flat bucket already holds zeros)
+            if w_hh is not None and ni[k + 1] and fused_grad_target(w_hh) is None:
+                d_whh = torch.zeros_like(w_hh)
             db = None
-            if (b_ih is not None and ni[k + 1]) or (b_hh is not None and ni[k + 2]):
+            if (b_ih is not None and ni[k + 2]) or (b_hh is not None and ni[k + 3]):
                 db = _colsum(dpre2)
             d_bih = d_bhh = None
-            if b_ih is not None and ni[k + 1]:
+            if b_ih is not None and ni[k + 2]:
                 d_bih = _into_or_return(db, b_ih)
-            if b_hh is not None and ni[k + 2]:
+            if b_hh is not None and ni[k + 3]:
                 d_bhh = _into_or_return(db, b_hh)
-            d_g = bgrad(g["dln_g"][l], ln_g) if ni[k + 3] else None
-            d_b = bgrad(g["dln_b"][l], ln_b) if ni[k + 4] else None
-            out += [d_wih, d_bih, d_bhh, d_g, d_b]
+            d_g = bgrad(g["dln_g"][l], ln_g) if ni[k + 4] else None
+            d_b = bgrad(g["dln_b"][l], ln_b) if ni[k + 5] else None
+            out += [d_wih, d_whh, d_bih, d_bhh, d_g, d_b]
         ctx.keep = None
         return (d_base, d_gt, None, None, None, d_wprev, d_w1, d_b1, d_w2, d_b2, *out)
 
@@ -178,6 +182,6 @@ def rollout(base: torch.Tensor, gt_prev: torch.Tensor, mask: Optional[torch.Tens
             layers: Sequence[Sequence[Optional[torch.Tensor]]], w1, b1, w2, b2, relu: bool = True,
             eps: float = 1e-5) -> torch.Tensor:
     """Time-major rollout: base [T,B,H], gt_prev [T,B,P], mask [T,B] (bool / uint8; mask[t] feeds pred[t] to step
-    t+1) or None, layers = [(w_ih [4H,H], b_ih, b_hh, ln_weight, ln_bias), ...] -> pred [T,B,P]."""
+    t+1) or None, layers = [(w_ih [4H,H], w_hh | None, b_ih, b_hh, ln_weight, ln_bias), ...] -> pred [T,B,P]."""
     flat = [t for lay in layers for t in lay]
     return _RolloutFn.apply(base, gt_prev, mask, bool(relu), float(eps), w_prev, w1, b1, w2, b2, *flat)
