@@ -252,11 +252,14 @@ int mrg_gru_backward(const float* dy, const float* dh_n, const float* reserve, c
 int mrg_debug_set_trace(unsigned long long* buf);
 
 /* Measurement hooks used by bench.py: number of kernels this library has launched since it was loaded,
- * and CUDA-event timing of the recurrent / GEMM launches on their own stream.  mrg_profile_read fills
- * ms[3], n[3] for {recurrent forward, recurrent backward, GEMM} and resets the record. */
+ * and CUDA-event timing of the recurrent / GEMM / rollout launches on their own stream.  mrg_profile_read fills
+ * ms[MRG_PROF_KINDS], n[MRG_PROF_KINDS] for {recurrent forward, recurrent backward, GEMM, rollout forward, rollout
+ * backward} and resets the record; mrg_profile_kernel_name(kind) names the last kernel of that kind that was timed. */
+#define MRG_PROF_KINDS 5
 unsigned long long mrg_launch_count(void);
 int mrg_profile_enable(int on);
 int mrg_profile_read(float* ms, int* n);
+const char* mrg_profile_kernel_name(int kind);
 
 #ifdef __cplusplus
 }

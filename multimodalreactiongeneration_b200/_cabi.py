@@ -19,7 +19,7 @@ EXPORTS = (
     "mrg_gemm_workspace_bytes", "mrg_layernorm_workspace_bytes", "mrg_residual_layernorm_forward",
     "mrg_residual_layernorm_backward", "mrg_adamw_flat", "mrg_debug_set_trace", "mrg_colsum", "mrg_colsum_workspace_bytes",
     "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
-    "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward",
+    "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward", "mrg_profile_kernel_name",
 )
 
 
@@ -56,6 +56,7 @@ class MrgError(RuntimeError):
 
 
 _LIB = None
+PROF_KINDS = ("rec_fwd", "rec_bwd", "gemm", "rollout_fwd", "rollout_bwd")
 
 
 def lib() -> ctypes.CDLL:
@@ -137,6 +138,8 @@ def lib() -> ctypes.CDLL:
     L.mrg_launch_count.restype = ctypes.c_ulonglong
     L.mrg_profile_enable.argtypes = [c_int]
     L.mrg_profile_read.argtypes = [POINTER(c_float), POINTER(c_int)]
+    L.mrg_profile_kernel_name.argtypes = [c_int]
+    L.mrg_profile_kernel_name.restype = c_char_p
     _LIB = L
     return L
 
@@ -150,11 +153,17 @@ def profile_enable(on: bool) -> None:
 
 
 def profile_read():
-    """-> {"rec_fwd": (ms, n), "rec_bwd": (ms, n), "gemm": (ms, n)} since profile_enable(True)."""
-    ms = (c_float * 3)()
-    n = (c_int * 3)()
+    """-> {"rec_fwd": (ms, n), "rec_bwd": .., "gemm": .., "rollout_fwd": .., "rollout_bwd": ..} since
+    profile_enable(True)."""
+    ms = (c_float * len(PROF_KINDS))()
+    n = (c_int * len(PROF_KINDS))()
     check(lib().mrg_profile_read(ms, n), "mrg_profile_read")
-    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("rec_fwd", "rec_bwd", "gemm"))}
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROF_KINDS)}
+
+
+def profile_kernel_name(kind: str) -> str:
+    """Demangled name of the last timed kernel of ``kind`` (one of PROF_KINDS), as the library launched it."""
+    return lib().mrg_profile_kernel_name(PROF_KINDS.index(kind)).decode()
 
 
 def check(status: int, what: str) -> None:

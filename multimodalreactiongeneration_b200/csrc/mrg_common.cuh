@@ -309,11 +309,11 @@ struct AttnArgs {
 // launch accounting / live kernel timing (bench.py's gpu_launches and roofline numbers)
 void count_launch(int n = 1);
 struct ProfScope {  // brackets a launch with CUDA events on its stream when profiling is enabled
-  ProfScope(int kind, cudaStream_t stream);
+  ProfScope(int kind, cudaStream_t stream, const char* kernel_name = nullptr);
   ~ProfScope();
   int slot;
   cudaStream_t stream;
 };
-enum { PROF_REC_FWD = 0, PROF_REC_BWD = 1, PROF_GEMM = 2, PROF_KINDS = 3 };
+enum { PROF_REC_FWD = 0, PROF_REC_BWD = 1, PROF_GEMM = 2, PROF_ROLLOUT_FWD = 3, PROF_ROLLOUT_BWD = 4, PROF_KINDS = 5 };
 
 }  // namespace mrg

@@ -24,11 +24,13 @@ constexpr int PROF_MAX = 8192;
 static cudaEvent_t g_ev[PROF_MAX][2];
 static int g_ev_kind[PROF_MAX];
 static int g_ev_created = 0, g_ev_used = 0;
+static char g_kind_name[PROF_KINDS][96];   // name of the last named kernel launched per kind
 
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
-ProfScope::ProfScope(int kind, cudaStream_t st) : slot(-1), stream(st) {
+ProfScope::ProfScope(int kind, cudaStream_t st, const char* name) : slot(-1), stream(st) {
   if (!g_prof_on || g_ev_used >= PROF_MAX) return;
+  if (name) snprintf(g_kind_name[kind], sizeof(g_kind_name[kind]), "%s", name);
   slot = g_ev_used++;
   if (slot >= g_ev_created) {
     cudaEventCreate(&g_ev[slot][0]);
@@ -227,8 +229,13 @@ extern "C" int mrg_profile_enable(int on) {
   return 0;
 }
 
+extern "C" const char* mrg_profile_kernel_name(int kind) {
+  return (kind >= 0 && kind < mrg::PROF_KINDS) ? mrg::g_kind_name[kind] : "";
+}
+
 // Sums the event-timed durations recorded since mrg_profile_enable(1): ms[k], n[k] for k in
-// {0: recurrent forward, 1: recurrent backward, 2: GEMM}.  Synchronises on the recorded events.
+// {0: recurrent forward, 1: recurrent backward, 2: GEMM, 3: rollout forward, 4: rollout backward}.
+// Synchronises on the recorded events.
 extern "C" int mrg_profile_read(float* ms, int* n) {
   for (int k = 0; k < mrg::PROF_KINDS; ++k) { ms[k] = 0.f; n[k] = 0; }
   for (int i = 0; i < mrg::g_ev_used; ++i) {

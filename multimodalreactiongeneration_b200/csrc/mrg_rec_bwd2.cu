@@ -376,7 +376,9 @@ static int launch_bwd2(const RecBwdArgs& a, int slices, int nch, cudaStream_t st
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(PROF_REC_BWD, stream);
+  static char name[64];
+  if (!name[0]) snprintf(name, sizeof(name), "mrg::rec_bwd2_kernel<%d, %d>", H, RBC);
+  ProfScope prof(PROF_REC_BWD, stream, name);
   count_launch();
   MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_bwd2_kernel<H, RBC>, a, slices, nch));
   return 0;

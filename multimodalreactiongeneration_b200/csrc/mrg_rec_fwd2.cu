@@ -325,7 +325,9 @@ static int launch_fwd2(const RecArgs& a, int slices, int nch, cudaStream_t strea
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(PROF_REC_FWD, stream);
+  static char name[64];
+  if (!name[0]) snprintf(name, sizeof(name), "mrg::rec_fwd2_kernel<%d, %d>", H, RBC);
+  ProfScope prof(PROF_REC_FWD, stream, name);
   count_launch();
   MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_fwd2_kernel<H, RBC>, a, slices, nch));
   return 0;

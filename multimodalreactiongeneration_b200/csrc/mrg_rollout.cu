@@ -797,7 +797,10 @@ static int ro_launch(RolloutArgs a, bool backward, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(backward ? PROF_REC_BWD : PROF_REC_FWD, stream);
+  static char name[2][64];
+  if (!name[backward][0])
+    snprintf(name[backward], sizeof(name[backward]), "mrg::rollout_%s_kernel<%d, %d>", backward ? "bwd" : "fwd", H, NL);
+  ProfScope prof(backward ? PROF_ROLLOUT_BWD : PROF_ROLLOUT_FWD, stream, name[backward]);
   count_launch();
   MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, a));
   return 0;

@@ -43,8 +43,10 @@ for mode in os.environ.get("MODES", "kernel,wavefront").split(","):
             torch.cuda.synchronize()
             p = _cabi.profile_read()
             _cabi.profile_enable(False)
-            print(f"   recurrent-class kernels in that step: fwd {p['rec_fwd'][0]:.2f} ms in {p['rec_fwd'][1]} launches, "
-                  f"bwd {p['rec_bwd'][0]:.2f} ms in {p['rec_bwd'][1]}; GEMM {p['gemm'][0]:.2f} ms in {p['gemm'][1]}", flush=True)
+            print(f"   kernels in that step: rollout fwd {p['rollout_fwd'][0]:.2f} ms ({1e3 * p['rollout_fwd'][0] / T:.2f} us/frame), "
+                  f"rollout bwd {p['rollout_bwd'][0]:.2f} ms ({1e3 * p['rollout_bwd'][0] / T:.2f} us/frame); sampler recurrence fwd "
+                  f"{p['rec_fwd'][0]:.2f} ms in {p['rec_fwd'][1]} launches, bwd {p['rec_bwd'][0]:.2f} ms in {p['rec_bwd'][1]}; "
+                  f"GEMM {p['gemm'][0]:.2f} ms in {p['gemm'][1]}", flush=True)
     if mode == "stepwise":
         continue
     m.eval()
@@ -59,5 +61,5 @@ for mode in os.environ.get("MODES", "kernel,wavefront").split(","):
             torch.cuda.synchronize()
             p = _cabi.profile_read()
             _cabi.profile_enable(False)
-            print(f"   free-running generation: recurrent-class kernels {p['rec_fwd'][0]:.2f} ms in {p['rec_fwd'][1]} launches "
-                  f"(sampler layers + rollout)", flush=True)
+            print(f"   free-running generation: rollout kernel {p['rollout_fwd'][0]:.2f} ms ({1e3 * p['rollout_fwd'][0] / T:.2f} us/frame), "
+                  f"sampler recurrence {p['rec_fwd'][0]:.2f} ms in {p['rec_fwd'][1]} launches", flush=True)
