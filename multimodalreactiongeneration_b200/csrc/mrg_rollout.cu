@@ -21,11 +21,21 @@
 // tile = 1 unit x H/16 k-values), the i rows in shared memory (one conflict-free LDS.128 per 4 k-values); the forget
 // rows are never loaded.  Per layer: FFMA2 partial sums -> shared-memory reduction over the k-slices -> gates + cell
 // update + residual (one warp per row, lane = unit) -> the 32 pre-LayerNorm values of every row are written into the
-// shared memory of ALL CTAs of the cluster (st.shared::cluster, 16 bytes per store) -> barrier.cluster -> every CTA
-// normalises the full row redundantly (it needs all H values as the next layer's input).  The bottleneck FFN is
-// split by output unit the same way; the pose, the feedback select and x_0 are computed redundantly per CTA (a few
-// hundred FMAs), so a step has NL + 1 cluster barriers and no other communication.  HBM sees only the per-step
-// inputs (base, ground-truth pose, mask) and, in training, the reserve for the backward.
+// shared memory of ALL CTAs of the cluster with 16-byte st.async stores that signal the destination's mbarrier
+// (complete_tx) -> every CTA waits for its own window to fill and normalises the full row redundantly (it needs all H
+// values as the next layer's input).  The bottleneck FFN is split by output unit the same way; the pose, the feedback
+// select and x_0 are computed redundantly per CTA (a few hundred FMAs), so a step has NL + 1 exchanges and no other
+// communication — no cluster barrier and no fence inside the time loop (the first version used barrier.cluster:
+// its release fence + arrive / wait round trip was 28 % of the kernel, profiles/r2_rollout_*).  HBM sees only the
+// per-step inputs (base, ground-truth pose, mask) and, in training, the reserve for the backward.
+//
+// Window reuse without extra synchronisation: the exchanges of a step use DIFFERENT windows in a fixed cyclic order
+// (v0, v1, f | stats, partials, ... , prev).  A peer can run at most one exchange ahead of this CTA — to send exchange
+// e+1 it must have completed the wait of exchange e, which needs this CTA's e data, which is sent only after this CTA
+// has consumed window e-1 — so a window is never written before its previous content was read, and an mbarrier never
+// receives bytes of its next phase before the current one completed.  Every window's mbarrier completes once per
+// step; it is re-armed (arrive.expect_tx) at the top of the step; bytes that land earlier only drive the
+// transaction count negative until then.
 //
 // Backward (rollout_bwd_kernel): the same clusters walk t = T-1 .. 0 with the chain dy -> FFN^T -> LN^T -> cell^T ->
 // W_ih^T -> ... -> W_prev^T -> (mask) -> dy_{t-1} (Q6: gradients flow through fed-back poses).  The transposed
@@ -94,7 +104,7 @@ __host__ __device__ inline int ro_align4(int n) { return (n + 3) & ~3; }
 // shared-memory layouts (offsets in floats, every block 16-byte aligned)
 // ---------------------------------------------------------------------------------------------------------
 struct RoFwdLayout {
-  int wi, part, xfull, vbuf, base, fbuf, fl, w1, w2, wprev, lng, lnb, bias, b1, b2, ysm, gtsm, msm, total;
+  int wi, part, xfull, vbuf, base, fbuf, fl, w1, w2, wprev, lng, lnb, bias, b1, b2, ysm, gtsm, msm, bars, total;
 };
 __host__ __device__ inline RoFwdLayout ro_fwd_layout(int H, int NL, int P, int FB) {
   const int CL = H / 32, KSL = H >= 64 ? 16 : 8, PP = P | 1, FBc = FB / CL;
@@ -118,8 +128,45 @@ __host__ __device__ inline RoFwdLayout ro_fwd_layout(int H, int NL, int P, int F
   l.ysm = o;   o += ro_align4(RO_RCAP * P);
   l.gtsm = o;  o += ro_align4(RO_RCAP * P);
   l.msm = o;   o += RO_RCAP;
+  l.bars = o;  o += 8;                              // mbarriers: v window 0, v window 1, FFN window (8 bytes each)
   l.total = o;
   return l;
+}
+
+// partial gate sums of NR rows over this thread's k-slice (forward mat-vec): i rows from shared memory, g / o rows
+// from registers; the two k sub-slices of a warp meet by shuffle, sub-slice s stores the rows r with (r & 1) == s
+template <int H, int NCH, int NR>
+__device__ __forceinline__ void ro_fwd_rows(const float4* __restrict__ wi_l, const float4 (&wg)[NCH],
+                                            const float4 (&wo)[NCH], const float* __restrict__ xrow, float* part_row,
+                                            int unit, int subk) {
+  float2 acc[3][NR];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) acc[g][r] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float4 wi = wi_l[c * 32 + unit];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const float4 x4 = *reinterpret_cast<const float4*>(xrow + r * H + 4 * c);
+      const float2 xlo = make_float2(x4.x, x4.y), xhi = make_float2(x4.z, x4.w);
+      ffma2(acc[0][r], make_float2(wi.x, wi.y), xlo);
+      ffma2(acc[0][r], make_float2(wi.z, wi.w), xhi);
+      ffma2(acc[1][r], make_float2(wg[c].x, wg[c].y), xlo);
+      ffma2(acc[1][r], make_float2(wg[c].z, wg[c].w), xhi);
+      ffma2(acc[2][r], make_float2(wo[c].x, wo[c].y), xlo);
+      ffma2(acc[2][r], make_float2(wo[c].z, wo[c].w), xhi);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float v = acc[g][r].x + acc[g][r].y;
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((r & 1) == subk) part_row[(r * 3 + g) * 32 + unit] = v;
+    }
 }
 
 // =========================================================================================================
@@ -153,6 +200,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
   float* ysm = sm + lay.ysm;
   float* gtsm = sm + lay.gtsm;
   float* msm = sm + lay.msm;
+  const uint32_t bar0 = smem_u32(sm + lay.bars);   // + 8 * window
   const int FBa = ro_align4(FB), FBca = ro_align4(FBc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -206,8 +254,14 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
   for (int idx = tid; idx < H * P; idx += RO_THREADS) wprev[(idx / P) * PP + idx % P] = a.w_prev[(size_t)(idx / P) * a.w_prev_ld + idx % P];
   for (int idx = tid; idx < FBc; idx += RO_THREADS) b1s[idx] = a.b1 ? a.b1[rank * FBc + idx] : 0.f;
   for (int idx = tid; idx < P; idx += RO_THREADS) b2s[idx] = a.b2 ? a.b2[idx] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(bar0 + 8 * i, 1);
+    mbar_init_fence();
+  }
   __syncthreads();
-  cluster_sync_all();  // every CTA of the cluster is resident before anybody writes into a peer's shared memory
+  cluster_sync_all();  // every CTA of the cluster is resident (and its mbarriers exist) before anybody sends to it
+  const uint32_t sm_base = smem_u32(sm);
+  uint32_t it = 0;  // steps done so far (all passes): every window's mbarrier completes once per step
 
   const int npass = (nrows + RC - 1) / RC;
   const int rpp = npass > 0 ? (nrows + npass - 1) / npass : 0;
@@ -224,6 +278,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
 
     for (int t = 0; t < T; ++t) {
       const size_t tb = (size_t)t * B + prow0;  // first row of this pass at step t
+      const uint32_t par = it & 1u;
+      ++it;
+      if (tid == 0) {  // this step's three exchanges: bytes every window will receive (all CTAs, itself included)
+#pragma unroll
+        for (int l = 0; l < NL; ++l) mbar_arrive_expect_tx(bar0 + 8 * (l & 1), (uint32_t)(R * H * 4));
+        mbar_arrive_expect_tx(bar0 + 16, (uint32_t)(R * FB * 4));
+      }
       // ================= phase A: previous pose, x_0 =================
       ro_cp_async_wait_all();
       __syncthreads();
@@ -254,41 +315,14 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
       for (int l = 0; l < NL; ++l) {
         // ================= phase B: partial gate sums over this thread's k-slice =================
         if (mv) {
-          for (int rg = 0; rg < R; rg += 4) {
-            float2 acc[3][4];
-#pragma unroll
-            for (int g = 0; g < 3; ++g)
-#pragma unroll
-              for (int r = 0; r < 4; ++r) acc[g][r] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-              const float4 wi = wi_sm[(l * (H / 4) + (k0 >> 2) + c) * 32 + unit];
-              const float4 wg = wr[l][0][c], wo = wr[l][1][c];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const float4 x4 = *reinterpret_cast<const float4*>(xfull + (rg + r) * H + k0 + 4 * c);
-                const float2 xlo = make_float2(x4.x, x4.y), xhi = make_float2(x4.z, x4.w);
-                ffma2(acc[0][r], make_float2(wi.x, wi.y), xlo);
-                ffma2(acc[0][r], make_float2(wi.z, wi.w), xhi);
-                ffma2(acc[1][r], make_float2(wg.x, wg.y), xlo);
-                ffma2(acc[1][r], make_float2(wg.z, wg.w), xhi);
-                ffma2(acc[2][r], make_float2(wo.x, wo.y), xlo);
-                ffma2(acc[2][r], make_float2(wo.z, wo.w), xhi);
-              }
-            }
-            // the two k sub-slices of a warp meet by shuffle; lanes 0-15 store rows rg, rg+1, lanes 16-31 rg+2, rg+3
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-              float s[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                s[r] = acc[g][r].x + acc[g][r].y;
-                s[r] += __shfl_xor_sync(0xffffffffu, s[r], 16);
-              }
-              const int rr = rg + subk * 2;
-              part[((ks * RC + rr) * 3 + g) * 32 + unit] = subk ? s[2] : s[0];
-              part[((ks * RC + rr + 1) * 3 + g) * 32 + unit] = subk ? s[3] : s[1];
-            }
+          const float4* wi_l = wi_sm + (l * (H / 4) + (k0 >> 2)) * 32;
+          for (int rg = 0; rg < R;) {   // row groups of 4, then a 2- or 1-row tail (no padded row slots)
+            const float* xrow = xfull + rg * H + k0;
+            float* prow = part + (ks * RC + rg) * 96;
+            const int left = R - rg;
+            if (left >= 3) { ro_fwd_rows<H, NCH, 4>(wi_l, wr[l][0], wr[l][1], xrow, prow, unit, subk); rg += 4; }
+            else if (left == 2) { ro_fwd_rows<H, NCH, 2>(wi_l, wr[l][0], wr[l][1], xrow, prow, unit, subk); rg += 2; }
+            else { ro_fwd_rows<H, NCH, 1>(wi_l, wr[l][0], wr[l][1], xrow, prow, unit, subk); rg += 1; }
           }
         }
         __syncthreads();
@@ -315,17 +349,21 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
           hv.y = __shfl_sync(0xffffffffu, v, (lane & ~3) + 1);
           hv.z = __shfl_sync(0xffffffffu, v, (lane & ~3) + 2);
           hv.w = __shfl_sync(0xffffffffu, v, (lane & ~3) + 3);
-          const uint32_t local = smem_u32(vwin + r * H + j0 + (lane & ~3));
+          const uint32_t off = smem_u32(vwin + r * H + j0 + (lane & ~3)) - sm_base;
+          const uint32_t boff = bar0 + 8 * (l & 1) - sm_base;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+          for (int i = 0; i < 2; ++i) {   // this lane's destinations: CTAs (lane & 3) and (lane & 3) + 4
             const int dst = (lane & 3) + 4 * i;
-            if (dst < CL) st_cluster_v4(map_to_cta(local, (uint32_t)dst), hv);
+            if (dst < CL) {
+              const uint32_t peer = map_to_cta(sm_base, (uint32_t)dst);
+              st_async_v4(peer + off, hv, peer + boff);
+            }
           }
         }
-        cluster_sync_all();
         // ================= phase D: LayerNorm of the full row (every CTA, redundantly) =================
         if (warp < R) {
           const int r = warp;
+          mbar_wait(bar0 + 8 * (l & 1), par);   // all CL slices of all R rows have landed in this CTA's window
           float v[H / 32];
           float s = 0.f;
 #pragma unroll
@@ -377,10 +415,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
         for (int i = tid; i < R * q4 * CL; i += RO_THREADS) {
           const int dst = i % CL, q = (i / CL) % q4, r = i / (CL * q4);
           const float4 v4 = *reinterpret_cast<const float4*>(fl + r * FBca + 4 * q);
-          st_cluster_v4(map_to_cta(smem_u32(fbuf + r * FBa + rank * FBc + 4 * q), (uint32_t)dst), v4);
+          const uint32_t peer = map_to_cta(sm_base, (uint32_t)dst);
+          st_async_v4(peer + (smem_u32(fbuf + r * FBa + rank * FBc + 4 * q) - sm_base), v4, peer + (bar0 + 16 - sm_base));
         }
       }
-      cluster_sync_all();
+      mbar_wait(bar0 + 16, par);   // the FFN hidden of all rows is complete in this CTA's window
       // ================= phase F: pose (every CTA), state for the next step =================
       for (int d0 = (tid >> 5) * 8; d0 < R * P; d0 += (RO_THREADS / 32) * 8) {  // warp-uniform trip count
         const int d = d0 + ((tid >> 2) & 7), sub = tid & 3;
@@ -409,7 +448,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
 // backward through time
 // =========================================================================================================
 struct RoBwdLayout {
-  int wi, part, dpre, dv, dx, rbuf, sbuf, pbuf, pl, w1t, w2, wprev, lng, pf, dysm, dfsm, dpn, total;
+  int wi, part, dpre, dv, dx, rbuf, sbuf, pbuf, pl, w1t, w2, wprev, lng, pf, dysm, dfsm, dpn, bars, total;
 };
 __host__ __device__ inline RoBwdLayout ro_bwd_layout(int H, int NL, int P, int FB) {
   const int CL = H / 32, PP = P | 1, P4 = ro_align4(P);
@@ -432,8 +471,39 @@ __host__ __device__ inline RoBwdLayout ro_bwd_layout(int H, int NL, int P, int F
   l.dysm = o;  o += ro_align4(RO_RCAP * P);
   l.dfsm = o;  o += RO_RCAP * ro_align4(FB);
   l.dpn = o;   o += ro_align4(RO_RCAP * P);  // d(prev) of the step processed before (t+1)
+  l.bars = o;  o += 2 * (2 * RO_LMAX + 1);   // mbarriers: row sums [layer], partials [layer], prev (8 bytes each)
   l.total = o;
   return l;
+}
+
+// partial dx of NR rows over this thread's 8 owned units (backward mat-vec): columns 2kp, 2kp+1
+template <int H, int NR>
+__device__ __forceinline__ void ro_bwd_rows(const float4* __restrict__ wi_l, const float2 (&wg)[4][2],
+                                            const float2 (&wo)[4][2], const float* __restrict__ drow, float* part_row) {
+  float2 acc[NR][2];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int jp = 0; jp < 4; ++jp) {
+    const float4 wi = wi_l[jp * (H / 2)];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const float* dr = drow + r * 96 + 2 * jp;
+      const float2 di = *reinterpret_cast<const float2*>(dr);
+      const float2 dg = *reinterpret_cast<const float2*>(dr + 32);
+      const float2 dd = *reinterpret_cast<const float2*>(dr + 64);
+      ffma2(acc[r][0], make_float2(wi.x, wi.y), di);
+      ffma2(acc[r][1], make_float2(wi.z, wi.w), di);
+      ffma2(acc[r][0], wg[jp][0], dg);
+      ffma2(acc[r][1], wg[jp][1], dg);
+      ffma2(acc[r][0], wo[jp][0], dd);
+      ffma2(acc[r][1], wo[jp][1], dd);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+    *reinterpret_cast<float2*>(part_row + r * H) =
+        make_float2(acc[r][0].x + acc[r][0].y, acc[r][1].x + acc[r][1].y);
 }
 
 template <int H, int NL>
@@ -462,6 +532,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
   float* dysm = sm + lay.dysm;
   float* dfsm = sm + lay.dfsm;
   float* dpn = sm + lay.dpn;
+  const uint32_t sm_base = smem_u32(sm);
+  const uint32_t bar0 = smem_u32(sm + lay.bars);
+  auto sbar = [&](int l) { return bar0 + 8u * (uint32_t)l; };             // row sums of layer l
+  auto rbar = [&](int l) { return bar0 + 8u * (uint32_t)(RO_LMAX + l); };   // partial dx of layer l
+  const uint32_t pbar = bar0 + 8u * (2 * RO_LMAX);                          // W_prev^T products
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_ctarank();
@@ -502,8 +577,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
   for (int idx = tid; idx < P * FB; idx += RO_THREADS) w2s[idx] = a.w2[idx];
   for (int idx = tid; idx < 32 * P; idx += RO_THREADS) wprev[(idx / P) * PP + idx % P] = a.w_prev[(size_t)(j0 + idx / P) * a.w_prev_ld + idx % P];
   for (int idx = tid; idx < NL * 32; idx += RO_THREADS) lng[idx] = a.ln_g[idx >> 5][j0 + (idx & 31)];
+  if (tid == 0) {
+    for (int i = 0; i < 2 * RO_LMAX + 1; ++i) mbar_init(bar0 + 8 * i, 1);
+    mbar_init_fence();
+  }
   __syncthreads();
   cluster_sync_all();
+  uint32_t it = 0;  // steps done so far (all passes): every mbarrier completes once per step
 
   const int npass = (nrows + RC - 1) / RC;
   const int rpp = npass > 0 ? (nrows + npass - 1) / npass : 0;
@@ -539,6 +619,16 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
 
     for (int t = T - 1; t >= 0; --t) {
       const size_t tb = (size_t)t * B + prow0;
+      const uint32_t par = it & 1u;
+      ++it;
+      if (tid == 0) {  // bytes every window of this step will receive (from all CL CTAs, itself included)
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+          mbar_arrive_expect_tx(sbar(l), (uint32_t)(CL * R * 8));
+          mbar_arrive_expect_tx(rbar(l), (uint32_t)(CL * R * 128));
+        }
+        mbar_arrive_expect_tx(pbar, (uint32_t)(CL * R * P4 * 4));
+      }
       // ================= phase 0: total gradient at the pose =================
       // mask[t] says whether y_t was fed to step t+1 (whose d(prev) sits in dpn)
       if (tid < R * P) {
@@ -598,15 +688,16 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
           dbet[l] += dxo;
           const float s1 = ro_warp_sum(gdx), s2 = ro_warp_sum(gdx * xh);
           if (lane < CL) {
-            const uint32_t addr = map_to_cta(smem_u32(sbuf + (rank * RC + r) * 2), (uint32_t)lane);
-            st_cluster_f32(addr, s1);
-            st_cluster_f32(addr + 4, s2);
+            const uint32_t peer = map_to_cta(sm_base, (uint32_t)lane);
+            const uint32_t addr = peer + (smem_u32(sbuf + (rank * RC + r) * 2) - sm_base);
+            st_async_f32(addr, s1, peer + (sbar(l) - sm_base));
+            st_async_f32(addr + 4, s2, peer + (sbar(l) - sm_base));
           }
         }
-        cluster_sync_all();
         // ================= phase 4: LayerNorm^T, cell^T (owned units) =================
         if (warp < R) {
           const int r = warp;
+          mbar_wait(sbar(l), par);   // the row sums of all CTAs have landed
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int c = 0; c < CL; ++c) { s1 += sbuf[(c * RC + r) * 2]; s2 += sbuf[(c * RC + r) * 2 + 1]; }
@@ -626,31 +717,14 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
         __syncthreads();
         // ================= phase 5: W_ih^T over the owned gate rows -> partial dx for every k =================
         if (mv) {
-          for (int rg = 0; rg < R; rg += 4) {
-            float2 acc[4][2];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {
-              const float4 wi = wi_sm[(l * 16 + jg * 4 + jp) * KP + kp];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const float* dr = dpre_sm + (rg + r) * 96 + 8 * jg + 2 * jp;
-                const float2 di = *reinterpret_cast<const float2*>(dr);
-                const float2 dg = *reinterpret_cast<const float2*>(dr + 32);
-                const float2 dd = *reinterpret_cast<const float2*>(dr + 64);
-                ffma2(acc[r][0], make_float2(wi.x, wi.y), di);
-                ffma2(acc[r][1], make_float2(wi.z, wi.w), di);
-                ffma2(acc[r][0], wr[l][0][jp][0], dg);
-                ffma2(acc[r][1], wr[l][0][jp][1], dg);
-                ffma2(acc[r][0], wr[l][1][jp][0], dd);
-                ffma2(acc[r][1], wr[l][1][jp][1], dd);
-              }
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              *reinterpret_cast<float2*>(part + (jg * RC + rg + r) * H + 2 * kp) =
-                  make_float2(acc[r][0].x + acc[r][0].y, acc[r][1].x + acc[r][1].y);
+          const float4* wi_l = wi_sm + (l * 16 + jg * 4) * KP + kp;
+          for (int rg = 0; rg < R;) {   // row groups of 4, then a 2- or 1-row tail
+            const float* drow = dpre_sm + rg * 96 + 8 * jg;
+            float* prow = part + (jg * RC + rg) * H + 2 * kp;
+            const int left = R - rg;
+            if (left >= 3) { ro_bwd_rows<H, 4>(wi_l, wr[l][0], wr[l][1], drow, prow); rg += 4; }
+            else if (left == 2) { ro_bwd_rows<H, 2>(wi_l, wr[l][0], wr[l][1], drow, prow); rg += 2; }
+            else { ro_bwd_rows<H, 1>(wi_l, wr[l][0], wr[l][1], drow, prow); rg += 1; }
           }
         }
         __syncthreads();
@@ -663,13 +737,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
             const float4 q = *reinterpret_cast<const float4*>(part + (g * RC + r) * H + k4);
             s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
           }
-          const uint32_t addr = map_to_cta(smem_u32(rbuf + (rank * RC + r) * 32 + (k4 & 31)), (uint32_t)(k4 >> 5));
-          st_cluster_v4(addr, s);
+          const uint32_t peer = map_to_cta(sm_base, (uint32_t)(k4 >> 5));
+          st_async_v4(peer + (smem_u32(rbuf + (rank * RC + r) * 32 + (k4 & 31)) - sm_base), s, peer + (rbar(l) - sm_base));
         }
-        cluster_sync_all();
         // ================= phase 6: gradient at the layer's input, owned units =================
         if (warp < R) {
           const int r = warp;
+          mbar_wait(rbar(l), par);   // the partial sums of all CTAs for this CTA's units have landed
           float s = dv_sm[r * 32 + lane];
 #pragma unroll
           for (int c = 0; c < CL; ++c) s += rbuf[(c * RC + r) * 32 + lane];
@@ -709,9 +783,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
       for (int i = tid; i < R * (P4 / 4) * CL; i += RO_THREADS) {
         const int dst = i % CL, q = (i / CL) % (P4 / 4), r = i / (CL * (P4 / 4));
         const float4 v4 = *reinterpret_cast<const float4*>(pl + r * P4 + 4 * q);
-        st_cluster_v4(map_to_cta(smem_u32(pbuf + (rank * RC + r) * P4 + 4 * q), (uint32_t)dst), v4);
+        const uint32_t peer = map_to_cta(sm_base, (uint32_t)dst);
+        st_async_v4(peer + (smem_u32(pbuf + (rank * RC + r) * P4 + 4 * q) - sm_base), v4, peer + (pbar - sm_base));
       }
-      cluster_sync_all();
+      mbar_wait(pbar, par);
       if (tid < R * P) {
         const int r = tid / P, p = tid % P;
         float s = 0.f;
