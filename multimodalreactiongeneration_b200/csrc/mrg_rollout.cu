@@ -99,12 +99,32 @@ __device__ __forceinline__ float ro_warp_sum(float v) {
   return v;
 }
 __host__ __device__ inline int ro_align4(int n) { return (n + 3) & ~3; }
+// n / d for n < 1024, d <= 64 with one multiply (inv = ro_inv(d)): the runtime divisors of the kernels (pose width,
+// bottleneck width) would otherwise put a ~130-clock integer division on the serial path of every step
+__host__ __device__ inline unsigned ro_inv(int d) { return ((1u << 20) + (unsigned)d - 1u) / (unsigned)d; }
+__device__ __forceinline__ int ro_div(int n, unsigned inv) { return (int)(((unsigned)n * inv) >> 20); }
+
+// Developer-only phase timing (-DMRG_RO_TRACE): thread 0 of CTA 0 accumulates the clocks it spends between the phase
+// marks of a step into a global array that mrg_debug_rollout_trace() copies out.
+#ifdef MRG_RO_TRACE
+__device__ unsigned long long g_ro_trace[2][32];
+#define RO_TRACE_DECL unsigned long long ro_t0 = clock64();
+#define RO_MARK(dir, k)                                                    \
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                               \
+    const unsigned long long ro_t1 = clock64();                            \
+    g_ro_trace[dir][k] += ro_t1 - ro_t0;                                   \
+    ro_t0 = ro_t1;                                                         \
+  }
+#else
+#define RO_TRACE_DECL
+#define RO_MARK(dir, k)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // shared-memory layouts (offsets in floats, every block 16-byte aligned)
 // ---------------------------------------------------------------------------------------------------------
 struct RoFwdLayout {
-  int wi, part, xfull, vbuf, base, fbuf, fl, w1, w2, wprev, lng, lnb, bias, b1, b2, ysm, gtsm, msm, bars, total;
+  int wi, part, xfull, vbuf, base, fbuf, w1, w2, wprev, lng, lnb, bias, b1, b2, prevsm, bars, total;
 };
 __host__ __device__ inline RoFwdLayout ro_fwd_layout(int H, int NL, int P, int FB) {
   const int CL = H / 32, KSL = H >= 64 ? 16 : 8, PP = P | 1, FBc = FB / CL;
@@ -116,7 +136,6 @@ __host__ __device__ inline RoFwdLayout ro_fwd_layout(int H, int NL, int P, int F
   l.vbuf = o;  o += 2 * RO_RCAP * H;                // pre-LayerNorm rows written by all CTAs (two windows)
   l.base = o;  o += RO_RCAP * H;                    // cp.async landing zone of base[t+1]
   l.fbuf = o;  o += RO_RCAP * ro_align4(FB);        // FFN hidden written by all CTAs
-  l.fl = o;    o += RO_RCAP * ro_align4(FBc);       // this CTA's part of it
   l.w1 = o;    o += ro_align4(FBc * H);
   l.w2 = o;    o += ro_align4(P * FB);
   l.wprev = o; o += ro_align4(H * PP);
@@ -125,9 +144,7 @@ __host__ __device__ inline RoFwdLayout ro_fwd_layout(int H, int NL, int P, int F
   l.bias = o;  o += NL * 3 * 32;
   l.b1 = o;    o += ro_align4(FBc);
   l.b2 = o;    o += ro_align4(P);
-  l.ysm = o;   o += ro_align4(RO_RCAP * P);
-  l.gtsm = o;  o += ro_align4(RO_RCAP * P);
-  l.msm = o;   o += RO_RCAP;
+  l.prevsm = o; o += ro_align4(RO_RCAP * P);        // the pose fed to the current step, transposed [p][row]
   l.bars = o;  o += 8;                              // mbarriers: v window 0, v window 1, FFN window (8 bytes each)
   l.total = o;
   return l;
@@ -188,7 +205,6 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
   float* vbuf = sm + lay.vbuf;
   float* basebuf = sm + lay.base;
   float* fbuf = sm + lay.fbuf;
-  float* fl = sm + lay.fl;
   float* w1s = sm + lay.w1;
   float* w2s = sm + lay.w2;
   float* wprev = sm + lay.wprev;
@@ -197,11 +213,11 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
   float* bias = sm + lay.bias;
   float* b1s = sm + lay.b1;
   float* b2s = sm + lay.b2;
-  float* ysm = sm + lay.ysm;
-  float* gtsm = sm + lay.gtsm;
-  float* msm = sm + lay.msm;
+  float* prevsm = sm + lay.prevsm;
   const uint32_t bar0 = smem_u32(sm + lay.bars);   // + 8 * window
-  const int FBa = ro_align4(FB), FBca = ro_align4(FBc);
+  const int FBa = ro_align4(FB);
+  constexpr int FIT = 4;   // rounds of phase F: 64 (row, pose) items per round, RO_RCAP * 32 items at most
+  const unsigned invP = ro_inv(P), invFBc = ro_inv(FBc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_ctarank();
@@ -262,6 +278,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
   cluster_sync_all();  // every CTA of the cluster is resident (and its mbarriers exist) before anybody sends to it
   const uint32_t sm_base = smem_u32(sm);
   uint32_t it = 0;  // steps done so far (all passes): every window's mbarrier completes once per step
+  RO_TRACE_DECL
 
   const int npass = (nrows + RC - 1) / RC;
   const int rpp = npass > 0 ? (nrows + npass - 1) / npass : 0;
@@ -270,11 +287,16 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
     const int prow0 = crow0 + pass * rpp;
     const int R = min(rpp, crow0 + nrows - prow0);
     // ---- state of step 0: ground-truth pose, no feedback; base[0] in flight ----
-    if (tid < R * P) gtsm[tid] = a.gt_prev[(size_t)prow0 * P + tid];
-    if (tid < RC) msm[tid] = 0.f;
+    for (int i = tid; i < RC * P; i += RO_THREADS) prevsm[i] = 0.f;   // rows beyond R stay finite
+    __syncthreads();
+    if (tid < R * P) {   // transposed window: prevsm[p][row]
+      const int r = ro_div(tid, invP), pp = tid - r * P;
+      prevsm[pp * RC + r] = a.gt_prev[(size_t)prow0 * P + tid];
+    }
     for (int e = tid; e < R * H / 4; e += RO_THREADS)
       ro_cp_async16(smem_u32(basebuf + 4 * e), a.base + (size_t)prow0 * H + 4 * e);
     ro_cp_async_commit();
+    const int nF = R * P;   // phase F items (row, pose component): 8 lanes each, 4 items per warp, <= FIT rounds
 
     for (int t = 0; t < T; ++t) {
       const size_t tb = (size_t)t * B + prow0;  // first row of this pass at step t
@@ -285,31 +307,46 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
         for (int l = 0; l < NL; ++l) mbar_arrive_expect_tx(bar0 + 8 * (l & 1), (uint32_t)(R * H * 4));
         mbar_arrive_expect_tx(bar0 + 16, (uint32_t)(R * FB * 4));
       }
-      // ================= phase A: previous pose, x_0 =================
+      // ================= phase A: x_0 = base + W_prev prev =================
       ro_cp_async_wait_all();
       __syncthreads();
-      for (int e = tid; e < R * H; e += RO_THREADS) {
-        const int r = e / H, k = e % H;
-        float acc = basebuf[e];
-        const float* wp = wprev + k * PP;
-        const bool fb = msm[r] != 0.f;
-        for (int p = 0; p < P; ++p) acc = fmaf(wp[p], fb ? ysm[r * P + p] : gtsm[r * P + p], acc);
-        xfull[e] = acc;
-        if (a.train && (k >> 5) == rank) a.xs[(tb + r) * H + k] = acc;
+      RO_MARK(0, 0)
+      // every phase that all 16 warps run costs (instructions x 4) issue cycles: one thread per column k computes all
+      // rows (one weight load + two 16-byte loads of the transposed pose window feed 8 FMAs)
+      if (tid < H) {
+        float acc[RC];
+#pragma unroll
+        for (int r = 0; r < RC; ++r) acc[r] = basebuf[r * H + tid];
+        const float* wp = wprev + tid * PP;
+        for (int p = 0; p < P; ++p) {
+          const float w = wp[p];
+          const float4 pa = *reinterpret_cast<const float4*>(prevsm + p * RC);
+          const float4 pb = *reinterpret_cast<const float4*>(prevsm + p * RC + 4);
+          acc[0] = fmaf(w, pa.x, acc[0]); acc[1] = fmaf(w, pa.y, acc[1]);
+          acc[2] = fmaf(w, pa.z, acc[2]); acc[3] = fmaf(w, pa.w, acc[3]);
+          acc[4] = fmaf(w, pb.x, acc[4]); acc[5] = fmaf(w, pb.y, acc[5]);
+          acc[6] = fmaf(w, pb.z, acc[6]); acc[7] = fmaf(w, pb.w, acc[7]);
+        }
+#pragma unroll
+        for (int r = 0; r < RC; ++r)
+          if (r < R) {
+            xfull[r * H + tid] = acc[r];
+            if (a.train && (tid >> 5) == rank) a.xs[(tb + r) * H + tid] = acc[r];
+          }
       }
-      if (a.train && rank == 0 && tid < R * P) {
-        const int r = tid / P;
-        a.prev[tb * P + tid] = msm[r] != 0.f ? ysm[tid] : gtsm[tid];
+      if (a.train && rank == 0 && tid < nF) {
+        const int r = ro_div(tid, invP), pp = tid - r * P;
+        a.prev[tb * P + tid] = prevsm[pp * RC + r];
       }
+      RO_MARK(0, 20)
       __syncthreads();
-      float gt_next = 0.f, m_next = 0.f;
-      if (t + 1 < T) {
+      RO_MARK(0, 21)
+      RO_MARK(0, 22)
+      if (t + 1 < T)
         for (int e = tid; e < R * H / 4; e += RO_THREADS)
           ro_cp_async16(smem_u32(basebuf + 4 * e), a.base + ((size_t)(t + 1) * B + prow0) * H + 4 * e);
-        if (tid < R * P) gt_next = a.gt_prev[((size_t)(t + 1) * B + prow0) * P + tid];
-        if (tid < R && a.mask) m_next = a.mask[tb + tid] ? 1.f : 0.f;
-      }
       ro_cp_async_commit();
+      RO_MARK(0, 1)
 
 #pragma unroll
       for (int l = 0; l < NL; ++l) {
@@ -325,7 +362,9 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
             else { ro_fwd_rows<H, NCH, 1>(wi_l, wr[l][0], wr[l][1], xrow, prow, unit, subk); rg += 1; }
           }
         }
+        RO_MARK(0, 2 + 5 * l)
         __syncthreads();
+        RO_MARK(0, 3 + 5 * l)
         // ================= phase C: gates, cell, residual; pre-LayerNorm values to every CTA =================
         float* vwin = vbuf + (l & 1) * RC * H;
         if (warp < R) {
@@ -360,19 +399,31 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
             }
           }
         }
+        RO_MARK(0, 4 + 5 * l)
         // ================= phase D: LayerNorm of the full row (every CTA, redundantly) =================
         if (warp < R) {
           const int r = warp;
           mbar_wait(bar0 + 8 * (l & 1), par);   // all CL slices of all R rows have landed in this CTA's window
+          RO_MARK(0, 5 + 5 * l)
+          // one butterfly for both moments: sums of (v - c) and (v - c)^2 around a sample c of the row (the row's
+          // first value), so that E[d^2] - E[d]^2 does not cancel (|c - mean| is a few sigma at most)
           float v[H / 32];
-          float s = 0.f;
 #pragma unroll
-          for (int i = 0; i < H / 32; ++i) { v[i] = vwin[r * H + lane + 32 * i]; s += v[i]; }
-          const float mean = ro_warp_sum(s) * (1.0f / H);
-          float q = 0.f;
+          for (int i = 0; i < H / 32; ++i) v[i] = vwin[r * H + lane + 32 * i];
+          const float c0 = __shfl_sync(0xffffffffu, v[0], 0);
+          float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int i = 0; i < H / 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-          const float rs = 1.0f / sqrtf(ro_warp_sum(q) * (1.0f / H) + a.eps);
+          for (int i = 0; i < H / 32; ++i) { const float d = v[i] - c0; s1 += d; s2 = fmaf(d, d, s2); }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          const float md = s1 * (1.0f / H);
+          const float mean = c0 + md;
+          const float var = fmaxf(fmaf(-md, md, s2 * (1.0f / H)), 0.f) + a.eps;
+          float rs = rsqrtf(var);
+          rs = rs * fmaf(-0.5f * var * rs, rs, 1.5f);   // one Newton step: full fp32 accuracy
 #pragma unroll
           for (int i = 0; i < H / 32; ++i) {
             const int k = lane + 32 * i;
@@ -387,56 +438,91 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_fwd_kernel(RolloutArgs 
           if (a.train && rank == 0 && lane == 0) a.rstd[(size_t)l * T * B + tb + r] = rs;
         }
         __syncthreads();
+        RO_MARK(0, 6 + 5 * l)
       }
 
-      // ================= phase E: bottleneck FFN, this CTA's FBc hidden units =================
-      for (int d0 = (tid >> 5) * 2; d0 < R * FBc; d0 += (RO_THREADS / 32) * 2) {  // warp-uniform trip count
-        const int d = d0 + ((tid >> 4) & 1), l16 = tid & 15;
-        const bool ok = d < R * FBc;
-        const int r = ok ? d / FBc : 0, o = ok ? d % FBc : 0;
-        float s = 0.f;
-        for (int k = l16 * 4; k < H; k += 64) {
-          const float4 w4 = *reinterpret_cast<const float4*>(w1s + o * H + k);
-          const float4 x4 = *reinterpret_cast<const float4*>(xfull + r * H + k);
-          s = fmaf(w4.x, x4.x, s); s = fmaf(w4.y, x4.y, s); s = fmaf(w4.z, x4.z, s); s = fmaf(w4.w, x4.w, s);
-        }
+      // loads for the feedback select at the end of this step, by the threads that use them.  Issued HERE, after the
+      // last mat-vec: values that are live across the register-hungry mat-vec get spilled right after the load, and
+      // the spill store waits for the load (a global round trip on the serial path — measured 860 clocks per step)
+      float gt_n[FIT];
+      unsigned m_n[FIT];
 #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (ok && l16 == 0) {
-          s += b1s[o];
-          if (a.relu) s = fmaxf(s, 0.f);
-          fl[r * FBca + o] = s;
-          if (a.train) a.fact[(tb + r) * FB + rank * FBc + o] = s;
+      for (int j = 0; j < FIT; ++j) {
+        gt_n[j] = 0.f;
+        m_n[j] = 0u;
+        if ((tid >> 5) * 4 + 64 * j >= nF) continue;   // warp-uniform: most warps have no item
+        const int item = (tid >> 5) * 4 + 64 * j + ((tid >> 3) & 3);
+        if ((tid & 7) == 0 && item < nF && t + 1 < T) {
+          const int r = ro_div(item, invP);
+          gt_n[j] = a.gt_prev[((size_t)(t + 1) * B + prow0) * P + item];
+          if (a.mask) m_n[j] = a.mask[tb + r];
         }
       }
-      __syncthreads();
-      {
-        const int q4 = FBc / 4;  // float4 pieces per row (FBc % 4 == 0, host-checked)
-        for (int i = tid; i < R * q4 * CL; i += RO_THREADS) {
-          const int dst = i % CL, q = (i / CL) % q4, r = i / (CL * q4);
-          const float4 v4 = *reinterpret_cast<const float4*>(fl + r * FBca + 4 * q);
-          const uint32_t peer = map_to_cta(sm_base, (uint32_t)dst);
-          st_async_v4(peer + (smem_u32(fbuf + r * FBa + rank * FBc + 4 * q) - sm_base), v4, peer + (bar0 + 16 - sm_base));
+      // ================= phase E: bottleneck FFN, this CTA's FBc hidden units =================
+      // 8 lanes per (row, unit) item, 4 items per warp = one float4 of the row, sent straight from registers
+      for (int i0 = (tid >> 5) * 4; i0 < R * FBc; i0 += (RO_THREADS / 32) * 4) {  // warp-uniform (R*FBc % 4 == 0)
+        const int l8 = tid & 7;
+        const int r = ro_div(i0, invFBc), o0 = i0 - r * FBc;
+        const int o = o0 + ((tid >> 3) & 3);
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int k = 0; k < H; k += 64) {
+          if (k + l8 * 4 < H) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w1s + o * H + k + l8 * 4);
+            const float4 x4 = *reinterpret_cast<const float4*>(xfull + r * H + k + l8 * 4);
+            sa = fmaf(w4.x, x4.x, sa); sa = fmaf(w4.y, x4.y, sa); sa = fmaf(w4.z, x4.z, sa); sa = fmaf(w4.w, x4.w, sa);
+          }
+          if (k + 32 + l8 * 4 < H) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w1s + o * H + k + 32 + l8 * 4);
+            const float4 x4 = *reinterpret_cast<const float4*>(xfull + r * H + k + 32 + l8 * 4);
+            sb = fmaf(w4.x, x4.x, sb); sb = fmaf(w4.y, x4.y, sb); sb = fmaf(w4.z, x4.z, sb); sb = fmaf(w4.w, x4.w, sb);
+          }
         }
+        float sv = sa + sb;
+        sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+        sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+        sv += b1s[o];
+        if (a.relu) sv = fmaxf(sv, 0.f);
+        float4 f4;
+        f4.x = __shfl_sync(0xffffffffu, sv, 0);
+        f4.y = __shfl_sync(0xffffffffu, sv, 8);
+        f4.z = __shfl_sync(0xffffffffu, sv, 16);
+        f4.w = __shfl_sync(0xffffffffu, sv, 24);
+        if (lane < CL) {
+          const uint32_t peer = map_to_cta(sm_base, (uint32_t)lane);
+          st_async_v4(peer + (smem_u32(fbuf + r * FBa + rank * FBc + o0) - sm_base), f4, peer + (bar0 + 16 - sm_base));
+        }
+        if (a.train && lane == 0) *reinterpret_cast<float4*>(a.fact + (tb + r) * FB + rank * FBc + o0) = f4;
       }
+      RO_MARK(0, 13)
       mbar_wait(bar0 + 16, par);   // the FFN hidden of all rows is complete in this CTA's window
-      // ================= phase F: pose (every CTA), state for the next step =================
-      for (int d0 = (tid >> 5) * 8; d0 < R * P; d0 += (RO_THREADS / 32) * 8) {  // warp-uniform trip count
-        const int d = d0 + ((tid >> 2) & 7), sub = tid & 3;
-        const bool ok = d < R * P;
-        const int r = ok ? d / P : 0, p = ok ? d % P : 0;
-        float s = 0.f;
-        for (int o = sub; o < FB; o += 4) s = fmaf(w2s[p * FB + o], fbuf[r * FBa + o], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (ok && sub == 0) {
-          s += b2s[p];
-          ysm[d] = s;
-          if (rank == 0) a.pred[tb * P + d] = s;
+      RO_MARK(0, 14)
+      // ================= phase F: pose (every CTA), feedback select for the next step =================
+#pragma unroll
+      for (int j = 0; j < FIT; ++j) {
+        const int i0 = (tid >> 5) * 4 + 64 * j;
+        if (i0 < nF) {   // warp-uniform
+          const int item = i0 + ((tid >> 3) & 3), l8 = tid & 7;
+          const bool ok = item < nF;
+          const int r = ok ? ro_div(item, invP) : 0, p = ok ? item - r * P : 0;
+          float sa = 0.f, sb = 0.f;
+          for (int o = l8; o < FB; o += 16) {
+            sa = fmaf(w2s[p * FB + o], fbuf[r * FBa + o], sa);
+            if (o + 8 < FB) sb = fmaf(w2s[p * FB + o + 8], fbuf[r * FBa + o + 8], sb);
+          }
+          float sv = sa + sb;
+          sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+          if (ok && l8 == 0) {
+            sv += b2s[p];
+            if (rank == 0) a.pred[tb * P + item] = sv;
+            prevsm[p * RC + r] = m_n[j] ? sv : gt_n[j];   // fed to step t+1 (read after the __syncthreads of phase A)
+          }
         }
       }
-      if (tid < R * P) gtsm[tid] = gt_next;   // read in phase A of this step, rewritten for the next one
-      if (tid < R) msm[tid] = m_next;
+      RO_MARK(0, 15)
       // (phase A of the next step starts with a __syncthreads)
     }
     __syncthreads();
@@ -467,7 +553,8 @@ __host__ __device__ inline RoBwdLayout ro_bwd_layout(int H, int NL, int P, int F
   l.w2 = o;    o += ro_align4(P * FB);
   l.wprev = o; o += ro_align4(32 * PP);      // W_prev rows of the owned units
   l.lng = o;   o += NL * 32;
-  l.pf = o;    o += NL * 4 * RO_RCAP * 32;   // cp.async landing zone: xhat, i, g, o of the next step to process
+  l.pf = o;                                  // cp.async landing zones (two steps): xhat, i, g, o, rstd, d(pose), FFN hidden
+  o += 2 * (NL * 4 * RO_RCAP * 32 + ro_align4(NL * RO_RCAP) + ro_align4(RO_RCAP * P) + RO_RCAP * ro_align4(FB));
   l.dysm = o;  o += ro_align4(RO_RCAP * P);
   l.dfsm = o;  o += RO_RCAP * ro_align4(FB);
   l.dpn = o;   o += ro_align4(RO_RCAP * P);  // d(prev) of the step processed before (t+1)
@@ -514,6 +601,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
   constexpr int MVT = 4 * KP;         // mat-vec threads (4 unit groups)
   extern __shared__ __align__(16) float sm[];
   const int P = a.P, FB = a.FB, PP = P | 1, P4 = ro_align4(P), FBa = ro_align4(FB), T = a.T, B = a.B;
+  const unsigned invP = ro_inv(P), invFB = ro_inv(FB), invP4q = ro_inv(P4 / 4);
   const RoBwdLayout lay = ro_bwd_layout(H, NL, P, FB);
   float4* wi_sm = reinterpret_cast<float4*>(sm + lay.wi);
   float* part = sm + lay.part;
@@ -584,6 +672,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
   __syncthreads();
   cluster_sync_all();
   uint32_t it = 0;  // steps done so far (all passes): every mbarrier completes once per step
+  RO_TRACE_DECL
 
   const int npass = (nrows + RC - 1) / RC;
   const int rpp = npass > 0 ? (nrows + npass - 1) / npass : 0;
@@ -595,26 +684,34 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
     for (int l = 0; l < NL; ++l) dgam[l] = dbet[l] = 0.f;
     if (tid < RC * P) dpn[tid] = 0.f;
     for (int i = tid; i < RC * P4; i += RO_THREADS) pl[i] = 0.f;   // the padding columns travel with the rest
-    // reserve of step T-1 for thread (row, unit): xhat, i, g, o of every layer
-    if (warp < R && T > 0) {
-      const size_t tb = (size_t)(T - 1) * B + prow0 + warp;
+    // reserve (xhat, i, g, o of every layer) for thread (row, unit), fetched with cp.async TWO steps ahead into
+    // alternating landing zones: one group per step, so the group of the step being processed is the older one
+    const int ZG = NL * 4 * RC * 32, ZR = ro_align4(NL * RC), ZP = ro_align4(RC * P);
+    const int ZSZ = ZG + ZR + ZP + RC * FBa;
+    auto fetch_reserve = [&](int ts) {
+      if (ts >= 0) {
+        float* z = pf + (ts & 1) * ZSZ;
+        const size_t tbp = (size_t)ts * B + prow0;
+        if (warp < R) {
+          const size_t tbn = tbp + warp;
 #pragma unroll
-      for (int l = 0; l < NL; ++l) {
-        ro_cp_async4(smem_u32(pf + ((l * 4 + 0) * RC + warp) * 32 + lane), a.xhat + (size_t)l * TBH + tb * H + j0 + lane);
-        const float* gp = a.gates + (((size_t)l * T * B + tb) * 3) * H + j0 + lane;
-        ro_cp_async4(smem_u32(pf + ((l * 4 + 1) * RC + warp) * 32 + lane), gp);
-        ro_cp_async4(smem_u32(pf + ((l * 4 + 2) * RC + warp) * 32 + lane), gp + H);
-        ro_cp_async4(smem_u32(pf + ((l * 4 + 3) * RC + warp) * 32 + lane), gp + 2 * H);
+          for (int l = 0; l < NL; ++l) {
+            ro_cp_async4(smem_u32(z + ((l * 4 + 0) * RC + warp) * 32 + lane), a.xhat + (size_t)l * TBH + tbn * H + j0 + lane);
+            const float* gp = a.gates + (((size_t)l * T * B + tbn) * 3) * H + j0 + lane;
+            ro_cp_async4(smem_u32(z + ((l * 4 + 1) * RC + warp) * 32 + lane), gp);
+            ro_cp_async4(smem_u32(z + ((l * 4 + 2) * RC + warp) * 32 + lane), gp + H);
+            ro_cp_async4(smem_u32(z + ((l * 4 + 3) * RC + warp) * 32 + lane), gp + 2 * H);
+            if (lane == 0) ro_cp_async4(smem_u32(z + ZG + l * RC + warp), a.rstd + (size_t)l * T * B + tbn);
+          }
+        }
+        if ((tid & ~31) < R * P && tid < R * P) ro_cp_async4(smem_u32(z + ZG + ZR + tid), a.dpred + tbp * P + tid);
+        if ((tid & ~31) < R * FB && tid < R * FB) ro_cp_async4(smem_u32(z + ZG + ZR + ZP + tid), a.fact + tbp * FB + tid);
       }
-    }
-    ro_cp_async_commit();
-    float dp_next = 0.f, m_cur = 0.f, f_cur = 0.f, rs_next[NL];
-    if (T > 0) {
-      if (tid < R * P) dp_next = a.dpred[((size_t)(T - 1) * B + prow0) * P + tid];
-      if (tid < R * FB) f_cur = a.fact[((size_t)(T - 1) * B + prow0 + tid / FB) * FB + tid % FB];
-#pragma unroll
-      for (int l = 0; l < NL; ++l) rs_next[l] = warp < R ? a.rstd[(size_t)l * T * B + (size_t)(T - 1) * B + prow0 + warp] : 0.f;
-    }
+      ro_cp_async_commit();
+    };
+    fetch_reserve(T - 1);
+    fetch_reserve(T - 2);
+    unsigned m_cur = 0u;   // raw byte of mask[t] for the step being processed (0 for t = T-1: nothing was fed on)
     __syncthreads();
 
     for (int t = T - 1; t >= 0; --t) {
@@ -629,48 +726,48 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
         }
         mbar_arrive_expect_tx(pbar, (uint32_t)(CL * R * P4 * 4));
       }
+      // the staged inputs of this step (issued two steps ago) have landed for everybody
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncthreads();
+      const float* z = pf + (t & 1) * ZSZ;
       // ================= phase 0: total gradient at the pose =================
       // mask[t] says whether y_t was fed to step t+1 (whose d(prev) sits in dpn)
       if (tid < R * P) {
-        const float dyv = dp_next + (m_cur != 0.f ? dpn[tid] : 0.f);
+        const float dyv = z[ZG + ZR + tid] + (m_cur != 0u ? dpn[tid] : 0.f);
         dysm[tid] = dyv;
         if (rank == 0) a.dy[tb * P + tid] = dyv;
       }
-      const float fval = f_cur;
-      float rs[NL];
-#pragma unroll
-      for (int l = 0; l < NL; ++l) rs[l] = rs_next[l];
-      // loads for step t-1, consumed one iteration later
-      if (t > 0) {
-        if (tid < R * P) dp_next = a.dpred[((size_t)(t - 1) * B + prow0) * P + tid];
-        if (tid < R * P && a.mask) m_cur = a.mask[(size_t)(t - 1) * B + prow0 + tid / P] ? 1.f : 0.f;
-        if (tid < R * FB) f_cur = a.fact[((size_t)(t - 1) * B + prow0 + tid / FB) * FB + tid % FB];
-#pragma unroll
-        for (int l = 0; l < NL; ++l) rs_next[l] = warp < R ? a.rstd[(size_t)l * T * B + (size_t)(t - 1) * B + prow0 + warp] : 0.f;
-      }
       __syncthreads();
+      RO_MARK(1, 0)
       // ================= phase 1: FFN hidden gradient (every CTA, all FB units) =================
       if (tid < R * FB) {
-        const int r = tid / FB, o = tid % FB;
+        const int r = ro_div(tid, invFB), o = tid - r * FB;
         float s = 0.f;
         for (int p = 0; p < P; ++p) s = fmaf(w2s[p * FB + o], dysm[r * P + p], s);
-        if (a.relu && !(fval > 0.f)) s = 0.f;
+        if (a.relu && !(z[ZG + ZR + ZP + tid] > 0.f)) s = 0.f;
         dfsm[r * FBa + o] = s;
         if (rank == 0) a.df[tb * FB + tid] = s;
       }
       __syncthreads();
+      RO_MARK(1, 1)
       // ================= phase 2: gradient at x_L, owned units =================
       for (int d0 = (tid >> 5) * 8; d0 < R * 32; d0 += (RO_THREADS / 32) * 8) {  // warp-uniform trip count
         const int d = d0 + ((tid >> 2) & 7), sub = tid & 3;
         const int r = d >> 5, k = d & 31;
-        float s = 0.f;
-        for (int o = sub; o < FB; o += 4) s = fmaf(w1t[o * 32 + k], dfsm[r * FBa + o], s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // independent chains: the loads pipeline
+        for (int o = sub; o < FB; o += 16) {
+          s0 = fmaf(w1t[o * 32 + k], dfsm[r * FBa + o], s0);
+          if (o + 4 < FB) s1 = fmaf(w1t[(o + 4) * 32 + k], dfsm[r * FBa + o + 4], s1);
+          if (o + 8 < FB) s2 = fmaf(w1t[(o + 8) * 32 + k], dfsm[r * FBa + o + 8], s2);
+          if (o + 12 < FB) s3 = fmaf(w1t[(o + 12) * 32 + k], dfsm[r * FBa + o + 12], s3);
+        }
+        float s = (s0 + s1) + (s2 + s3);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         if (sub == 0) dx_sm[d] = s;
       }
-      ro_cp_async_wait_all();  // reserve of this step (issued one step ago by the same thread)
       __syncthreads();
+      RO_MARK(1, 2)
 
 #pragma unroll
       for (int l = NL - 1; l >= 0; --l) {
@@ -679,10 +776,10 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
         if (warp < R) {
           const int r = warp;
           const float dxo = dx_sm[r * 32 + lane];
-          xh = pf[((l * 4 + 0) * RC + r) * 32 + lane];
-          gi = pf[((l * 4 + 1) * RC + r) * 32 + lane];
-          gg = pf[((l * 4 + 2) * RC + r) * 32 + lane];
-          go = pf[((l * 4 + 3) * RC + r) * 32 + lane];
+          xh = z[((l * 4 + 0) * RC + r) * 32 + lane];
+          gi = z[((l * 4 + 1) * RC + r) * 32 + lane];
+          gg = z[((l * 4 + 2) * RC + r) * 32 + lane];
+          go = z[((l * 4 + 3) * RC + r) * 32 + lane];
           gdx = dxo * lng[l * 32 + lane];
           dgam[l] = fmaf(dxo, xh, dgam[l]);
           dbet[l] += dxo;
@@ -694,14 +791,16 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
             st_async_f32(addr + 4, s2, peer + (sbar(l) - sm_base));
           }
         }
+        RO_MARK(1, 3 + 6 * l)
         // ================= phase 4: LayerNorm^T, cell^T (owned units) =================
         if (warp < R) {
           const int r = warp;
           mbar_wait(sbar(l), par);   // the row sums of all CTAs have landed
+          RO_MARK(1, 4 + 6 * l)
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int c = 0; c < CL; ++c) { s1 += sbuf[(c * RC + r) * 2]; s2 += sbuf[(c * RC + r) * 2 + 1]; }
-          const float dv = rs[l] * (gdx - s1 * (1.0f / H) - xh * s2 * (1.0f / H));
+          const float dv = z[ZG + l * RC + r] * (gdx - s1 * (1.0f / H) - xh * s2 * (1.0f / H));
           const float c = gi * gg, tc = fast_tanh(c);
           const float d_o = dv * tc * go * (1.f - go);
           const float dc = dv * go * (1.f - tc * tc);
@@ -715,6 +814,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
           dp[0] = d_i; dp[H] = 0.f; dp[2 * H] = d_g; dp[3 * H] = d_o;
         }
         __syncthreads();
+        RO_MARK(1, 5 + 6 * l)
         // ================= phase 5: W_ih^T over the owned gate rows -> partial dx for every k =================
         if (mv) {
           const float4* wi_l = wi_sm + (l * 16 + jg * 4) * KP + kp;
@@ -728,6 +828,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
           }
         }
         __syncthreads();
+        RO_MARK(1, 6 + 6 * l)
         // sum the 4 unit groups and hand every k to the CTA that owns it (window slot = this CTA's rank)
         for (int i = tid; i < R * (H / 4); i += RO_THREADS) {
           const int r = i / (H / 4), k4 = (i % (H / 4)) * 4;
@@ -740,10 +841,12 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
           const uint32_t peer = map_to_cta(sm_base, (uint32_t)(k4 >> 5));
           st_async_v4(peer + (smem_u32(rbuf + (rank * RC + r) * 32 + (k4 & 31)) - sm_base), s, peer + (rbar(l) - sm_base));
         }
+        RO_MARK(1, 7 + 6 * l)
         // ================= phase 6: gradient at the layer's input, owned units =================
         if (warp < R) {
           const int r = warp;
           mbar_wait(rbar(l), par);   // the partial sums of all CTAs for this CTA's units have landed
+          RO_MARK(1, 8 + 6 * l)
           float s = dv_sm[r * 32 + lane];
 #pragma unroll
           for (int c = 0; c < CL; ++c) s += rbuf[(c * RC + r) * 32 + lane];
@@ -753,24 +856,13 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
         // dx_sm is read next by the same thread (phase 3 of layer l-1) or after the barrier below (phase 7)
       }
       __syncthreads();
-      // reserve of step t-1 into the landing zone just consumed
-      if (t > 0 && warp < R) {
-        const size_t tbn = (size_t)(t - 1) * B + prow0 + warp;
-#pragma unroll
-        for (int l = 0; l < NL; ++l) {
-          ro_cp_async4(smem_u32(pf + ((l * 4 + 0) * RC + warp) * 32 + lane), a.xhat + (size_t)l * TBH + tbn * H + j0 + lane);
-          const float* gp = a.gates + (((size_t)l * T * B + tbn) * 3) * H + j0 + lane;
-          ro_cp_async4(smem_u32(pf + ((l * 4 + 1) * RC + warp) * 32 + lane), gp);
-          ro_cp_async4(smem_u32(pf + ((l * 4 + 2) * RC + warp) * 32 + lane), gp + H);
-          ro_cp_async4(smem_u32(pf + ((l * 4 + 3) * RC + warp) * 32 + lane), gp + 2 * H);
-        }
-      }
-      ro_cp_async_commit();
+      fetch_reserve(t - 2);   // into the landing zone just consumed (read by the same threads)
+      RO_MARK(1, 15)
       // ================= phase 7: W_prev^T over the owned units, all-reduced =================
       for (int d0 = (tid >> 5) * 4; d0 < R * P; d0 += (RO_THREADS / 32) * 4) {  // warp-uniform trip count
         const int d = d0 + ((tid >> 3) & 3), sub = tid & 7;
         const bool ok = d < R * P;
-        const int r = ok ? d / P : 0, p = ok ? d % P : 0;
+        const int r = ok ? ro_div(d, invP) : 0, p = ok ? d - r * P : 0;
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s = fmaf(wprev[(sub + 8 * i) * PP + p], dx_sm[r * 32 + sub + 8 * i], s);
@@ -781,22 +873,26 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_bwd_kernel(RolloutArgs 
       }
       __syncthreads();
       for (int i = tid; i < R * (P4 / 4) * CL; i += RO_THREADS) {
-        const int dst = i % CL, q = (i / CL) % (P4 / 4), r = i / (CL * (P4 / 4));
+        const int dst = i % CL, rq = i / CL, r = ro_div(rq, invP4q), q = rq - r * (P4 / 4);
         const float4 v4 = *reinterpret_cast<const float4*>(pl + r * P4 + 4 * q);
         const uint32_t peer = map_to_cta(sm_base, (uint32_t)dst);
         st_async_v4(peer + (smem_u32(pbuf + (rank * RC + r) * P4 + 4 * q) - sm_base), v4, peer + (pbar - sm_base));
       }
+      RO_MARK(1, 16)
       mbar_wait(pbar, par);
+      RO_MARK(1, 17)
       if (tid < R * P) {
-        const int r = tid / P, p = tid % P;
+        const int r = ro_div(tid, invP), p = tid - r * P;
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < CL; ++c) s += pbuf[(c * RC + r) * P4 + p];
         dpn[tid] = s;
         if (rank == 0) a.dprev[tb * P + tid] = s;
+        // mask[t-1] for the next iteration: loaded after the last mat-vec so that it is never live across one
+        m_cur = (a.mask && t > 0) ? a.mask[(size_t)(t - 1) * B + prow0 + r] : 0u;
       }
-      // (phase 0 of the next iteration reads dpn after its own __syncthreads ... see below)
       __syncthreads();
+      RO_MARK(1, 18)
     }
     if (warp < R) {
 #pragma unroll
@@ -934,6 +1030,17 @@ static int ro_check(const char* who, const mrg_rollout_weights* w, int T, int B)
 }  // namespace mrg
 
 using namespace mrg;
+
+#ifdef MRG_RO_TRACE
+extern "C" int mrg_debug_rollout_trace(unsigned long long* out, int reset) {  // out[2][32] host array
+  MRG_CUDA_CHECK(cudaMemcpyFromSymbol(out, mrg::g_ro_trace, sizeof(unsigned long long) * 64));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    MRG_CUDA_CHECK(cudaMemcpyToSymbol(mrg::g_ro_trace, z, sizeof(z)));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int mrg_rollout_supported(int H, int L, int P, int FB) { return ro_shape_ok(H, L, P, FB) ? 1 : 0; }
 
