@@ -24,7 +24,7 @@
  *   x       [T][B][I]            time-major input of the layer
  *   w_ih    [4H][I], w_hh [4H][H], b_* [4H]   torch.nn.LSTM layout, gate order i,f,g,o (rnn.py:842-847)
  *   gates   [D][T][B][H][4]      reserve: post-activation (i,f,g,o) per hidden unit, gate-interleaved;
- *                                the backward overwrites it with d(pre-activation)
+ *                                the backward overwrites it with d(pre-activation); fp32, or bfloat16 with MRG_F_BF16
  *   y_ext   [D][T+1][B][H]       hidden states with one extra slot for h0:
  *                                  direction 0 (forward in time): slot 0 = h0, slot t+1 = h_t
  *                                  direction 1 (reverse):          slot T = h0, slot t   = h_t
@@ -54,6 +54,11 @@ extern "C" {
 #define MRG_F_TF32        32   /* reduced-precision mode: the projection GEMMs run ONE tf32 tensor-core
                                   pass (10-bit mantissa, >= bf16 precision) instead of the 3-pass
                                   fp32-grade split; the recurrence itself stays fp32               */
+#define MRG_F_BF16        64   /* bf16 mode (with MRG_F_TF32): the reserve `gates` holds 4 x bfloat16 per hidden unit
+                                  (8 bytes: x-projection in, gates out, d(pre-activations) back) — half the bytes of
+                                  the largest buffer of the path; the GEMMs around it take / write bfloat16 and run one
+                                  tf32 tensor-core pass (bf16 values are exact in tf32), accumulation and the
+                                  recurrence stay fp32.  Cluster kernels only: H in {128, 256}, T > 1               */
 #define MRG_F_CLUSTER_BUDGET(n) (((n) & 0xFF) << 16)  /* recurrent kernels use at most n clusters (0 = all): lets two
                                   independent LSTM stacks (audio / motion encoders) run side by side on two streams */
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that

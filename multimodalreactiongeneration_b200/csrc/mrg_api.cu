@@ -14,7 +14,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int run_gemm(const GemmArgs& g_in, void* ws, size_t ws_bytes, int flags, cudaStream_t stream) {
   GemmArgs g = g_in;
-  g.single_pass = (flags & MRG_F_TF32) ? 1 : 0;
+  g.single_pass = (flags & (MRG_F_TF32 | MRG_F_BF16)) ? 1 : 0;
   if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) return gemm_tc2(g, ws, ws_bytes, stream);
   return gemm_simt(g, ws, ws_bytes, stream);
 }
@@ -94,6 +94,9 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     set_error("mrg_lstm_layer_forward: workspace too small");
     return MRG_E_WORKSPACE;
   }
+  const bool bf16 = (flags & MRG_F_BF16) != 0;
+  MRG_REQUIRE(!bf16 || (T > 1 && rec2_supported(H) && !(flags & MRG_F_GENERIC_REC)),
+              "mrg_lstm_layer_forward: MRG_F_BF16 needs the cluster kernels (H in {128, 256}, T > 1)");
   char* ws = (char*)workspace;
   float* bias_pack = (float*)ws;
   ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
@@ -125,7 +128,10 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     g.a = x; g.a_sm = I; g.a_sk = 1;
     g.b = w_pack + (size_t)d * 4 * H * I; g.b_sk = 1; g.b_sn = I;
     g.bias = bias_pack + (size_t)d * 4 * H;
-    g.c = gates + (size_t)d * T * B * 4 * H; g.ldc = 4 * H;
+    // bf16 mode: the reserve is bfloat16, direction d starts half as many bytes in
+    g.c = bf16 ? reinterpret_cast<float*>(reinterpret_cast<unsigned short*>(gates) + (size_t)d * T * B * 4 * H)
+               : gates + (size_t)d * T * B * 4 * H;
+    g.ldc = 4 * H; g.c_bf16 = bf16 ? 1 : 0;
     g.M = T * B; g.N = 4 * H; g.K = I;
     if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
   }
@@ -152,6 +158,7 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   r.train = (flags & MRG_F_TRAIN) ? 1 : 0;
   r.trace = debug_trace_buffer();
   r.cluster_budget = (flags >> 16) & 0xFF;
+  r.bf16_gates = bf16 ? 1 : 0;
   if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
   return rec_forward_generic(r, stream);
 }
@@ -169,6 +176,9 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
     set_error("mrg_lstm_layer_backward: workspace too small");
     return MRG_E_WORKSPACE;
   }
+  const bool bf16 = (flags & MRG_F_BF16) != 0;
+  MRG_REQUIRE(!bf16 || (T > 1 && rec2_supported(H) && !(flags & MRG_F_GENERIC_REC)),
+              "mrg_lstm_layer_backward: MRG_F_BF16 needs the cluster kernels (H in {128, 256}, T > 1)");
   char* ws = (char*)workspace;
   ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
   float* db_part = (float*)ws;
@@ -191,6 +201,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   r.db_part = db_part;
   r.T = T; r.B = B; r.H = H; r.D = D;
   r.cluster_budget = (flags >> 16) & 0xFF;
+  r.bf16_gates = bf16 ? 1 : 0;
   int e = 0;
   // two-phase backward: MRG_F_BWD_NO_WGRAD = BPTT + bias sums + dX (what the previous layer waits for),
   // MRG_F_BWD_WGRAD_ONLY = the two weight-gradient GEMMs from the d(pre-activations) an earlier NO_WGRAD call left in
@@ -206,7 +217,9 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
 
   const size_t slot = (size_t)B * H;
   for (int d = 0; d < D; ++d) {
-    const float* dpre = gates + (size_t)d * T * B * 4 * H;
+    const float* dpre = bf16 ? reinterpret_cast<const float*>(reinterpret_cast<const unsigned short*>(gates) +
+                                                               (size_t)d * T * B * 4 * H)
+                             : gates + (size_t)d * T * B * 4 * H;
     if (g[d].db && do_rec)
       if ((e = colsum_deinterleave(db_part + (size_t)d * B * 4 * H, g[d].db, B, H, acc_b, stream))) return e;
     if (g[d].dw_ih && do_wgrad) {
@@ -215,7 +228,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       m.b = x; m.b_sk = I; m.b_sn = 1;
       m.c = g[d].dw_ih; m.ldc = I;
       m.M = 4 * H; m.N = I; m.K = T * B;
-      m.accumulate = acc; m.row_deinterleave_H = H;
+      m.accumulate = acc; m.row_deinterleave_H = H; m.a_bf16 = bf16 ? 1 : 0;
       if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
     }
     if (!do_wgrad) {
@@ -228,7 +241,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       m.b = hprev; m.b_sk = H; m.b_sn = 1;
       m.c = g[d].dw_hh; m.ldc = H;
       m.M = 4 * H; m.N = H; m.K = T * B;
-      m.accumulate = acc; m.row_deinterleave_H = H;
+      m.accumulate = acc; m.row_deinterleave_H = H; m.a_bf16 = bf16 ? 1 : 0;
       if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
     }
     if (dx && do_rec) {
@@ -237,7 +250,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       m.b = w_pack + (size_t)d * 4 * H * I; m.b_sk = I; m.b_sn = 1;
       m.c = dx; m.ldc = I;
       m.M = T * B; m.N = I; m.K = 4 * H;
-      m.accumulate = d > 0 ? 1 : 0;
+      m.accumulate = d > 0 ? 1 : 0; m.a_bf16 = bf16 ? 1 : 0;
       if ((e = run_gemm(m, ws, ws_left, flags, stream))) return e;
     }
   }

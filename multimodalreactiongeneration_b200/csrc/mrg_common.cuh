@@ -240,7 +240,24 @@ struct GemmArgs {
   int accumulate;      // C += result
   int row_deinterleave_H;  // >0: output row m=(j*4+g) is stored at row g*H+j (gate de-interleave)
   int single_pass;         // tensor-core path only: one tf32 pass (MRG_F_TF32) instead of 3xTF32
+  int a_bf16;              // bf16 mode: the A operand is stored as bfloat16 (a points to uint16 data, strides in elements)
+  int c_bf16;              // bf16 mode: C is stored as bfloat16 (round to nearest even); no accumulate, no de-interleave
 };
+
+// bfloat16 storage helpers of the bf16 mode (the reserve of the recurrent kernels and the GEMM operands next to it)
+__device__ __forceinline__ float bf16_lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // low half = lo, high half = hi (RNE)
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+  return make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 v) {
+  return make_float4(bf16_lo_to_f32(v.x), bf16_hi_to_f32(v.x), bf16_lo_to_f32(v.y), bf16_hi_to_f32(v.y));
+}
 
 int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_simt_workspace_bytes(int M, int N, int K);
@@ -257,6 +274,7 @@ struct RecArgs {
   int train;
   unsigned long long* trace;  // developer event trace (-DMRG_REC_TRACE builds), else nullptr
   int cluster_budget;         // > 0: use at most this many clusters (MRG_F_CLUSTER_BUDGET)
+  int bf16_gates;             // bf16 mode: `gates` holds 4 x bfloat16 per hidden unit (8 bytes) instead of 4 x fp32
 };
 unsigned long long* debug_trace_buffer();
 int rec_forward_generic(const RecArgs& a, cudaStream_t stream);
@@ -274,6 +292,7 @@ struct RecBwdArgs {
   float* db_part;       // [D][B][H][4] per-row bias-gradient partials (sum over t)
   int T, B, H, D;
   int cluster_budget;   // same meaning as in RecArgs
+  int bf16_gates;       // same meaning as in RecArgs: gates in, d(pre-activations) out, both bfloat16
 };
 int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 // cluster kernels (chunk-pipelined, H in {128, 256})

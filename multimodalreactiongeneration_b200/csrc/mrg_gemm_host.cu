@@ -15,6 +15,10 @@ __global__ void tc_splitk_reduce_kernel(TcParams p, int splits) {
   for (int s = 0; s < splits; ++s) v += p.partial[(size_t)s * p.M * p.N + idx];
   if (p.bias) v += p.bias[n];
   const int row = p.deint_H > 0 ? ((m & 3) * p.deint_H + (m >> 2)) : m;
+  if (p.c_bf16) {
+    reinterpret_cast<unsigned short*>(p.c)[(long long)row * p.ldc + n] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xFFFFu);
+    return;
+  }
   float* o = p.c + (long long)row * p.ldc + n;
   *o = p.accumulate ? *o + v : v;
 }
@@ -45,45 +49,52 @@ static EncodeTiledFn get_encode_fn() {
 // operand X(r, k): element (r,k) at ptr[r*s_r + k*s_k]; K-major if s_k == 1, MN-major if s_r == 1
 // `plain_mn`: an MN-major operand that is read element-wise by converter threads (the TMEM-operand kernel) is
 // loaded without swizzle (box = 32 rows x 32 k, 4 boxes per tile).
+// `bf16`: the operand is stored as bfloat16 (only for an A operand that goes through the converter warps: plain tiles,
+// 64-byte rows, no swizzle).
 int make_tc_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k, int rows, int K, int* mn_major,
-                int plain_mn) {
+                int plain_mn, int bf16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return MRG_E_UNSUPPORTED; }
   cuuint64_t dims[2], strides[1];
   cuuint32_t box[2], estr[2] = {1, 1};
+  const cuuint64_t esz = bf16 ? 2 : 4;
   if (s_k == 1) {           // K-major: inner = K
     *mn_major = 0;
     dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
-    strides[0] = (cuuint64_t)s_r * 4;
+    strides[0] = (cuuint64_t)s_r * esz;
     box[0] = TBK; box[1] = TBM;
   } else {                  // MN-major: inner = rows
     *mn_major = 1;
     dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
-    strides[0] = (cuuint64_t)s_k * 4;
+    strides[0] = (cuuint64_t)s_k * esz;
     box[0] = 32; box[1] = TBK;
   }
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         *mn_major ? (plain_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-                                   : CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapSwizzle swz =
+      bf16 ? CU_TENSOR_MAP_SWIZZLE_NONE
+           : (*mn_major ? (plain_mn ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                        : CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr,
+                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MRG_E_INVALID; }
   return 0;
 }
 
-static bool operand_ok(const float* ptr, long long s_r, long long s_k) {
+static bool operand_ok(const float* ptr, long long s_r, long long s_k, int bf16 = 0) {
   if (((uintptr_t)ptr & 15) != 0) return false;
-  if (s_k == 1) return s_r >= 4 && s_r % 4 == 0;
-  if (s_r == 1) return s_k >= 4 && s_k % 4 == 0;
+  const long long q = bf16 ? 8 : 4;   // global strides must be multiples of 16 bytes
+  if (s_k == 1) return s_r >= q && s_r % q == 0;
+  if (s_r == 1) return s_k >= q && s_k % q == 0;
   return false;
 }
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return false;
-  if (g.N % 4 != 0 || g.ldc % 4 != 0 || ((uintptr_t)g.c & 15) != 0) return false;
+  if (g.N % 4 != 0 || g.ldc % 4 != 0 || ((uintptr_t)g.c & (g.c_bf16 ? 7 : 15)) != 0) return false;
+  if (g.c_bf16 && (g.accumulate || g.row_deinterleave_H > 0)) return false;
   if (g.bias && ((uintptr_t)g.bias & 15) != 0) return false;
   if ((long long)g.M * g.N < 64 * 64) return false;  // tiny problems: SIMT path
-  return operand_ok(g.a, g.a_sm, g.a_sk) && operand_ok(g.b, g.b_sn, g.b_sk) && get_encode_fn() != nullptr;
+  return operand_ok(g.a, g.a_sm, g.a_sk, g.a_bf16) && operand_ok(g.b, g.b_sn, g.b_sk) && get_encode_fn() != nullptr;
 }
 
 int tc_splits(int M, int N, int K) {

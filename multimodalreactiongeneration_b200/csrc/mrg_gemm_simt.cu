@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g, float* __res
       int m, k;
       if (A_KCONTIG) { k = e % BK; m = e / BK; } else { m = e % BM; k = e / BM; }
       const int gm = m0 + m, gk = k0 + k;
-      ra[i] = (gm < g.M && gk < kend) ? g.a[(long long)gm * g.a_sm + (long long)gk * g.a_sk] : 0.f;
+      const long long ai = (long long)gm * g.a_sm + (long long)gk * g.a_sk;
+      ra[i] = (gm < g.M && gk < kend)
+                  ? (g.a_bf16 ? bf16_lo_to_f32(reinterpret_cast<const unsigned short*>(g.a)[ai]) : g.a[ai])
+                  : 0.f;
       int n, kb;
       if (B_NCONTIG) { n = e % BN; kb = e / BN; } else { kb = e % BK; n = e / BK; }
       const int gn = n0 + n, gkb = k0 + kb;
@@ -85,8 +88,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g, float* __res
         const int r = g.row_deinterleave_H > 0 ? ((m & 3) * g.row_deinterleave_H + (m >> 2)) : m;
         float v = acc[i][j];
         if (g.bias) v += g.bias[n];
-        float* o = g.c + (long long)r * g.ldc + n;
-        *o = g.accumulate ? *o + v : v;
+        if (g.c_bf16) {
+          reinterpret_cast<unsigned short*>(g.c)[(long long)r * g.ldc + n] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xFFFFu);
+        } else {
+          float* o = g.c + (long long)r * g.ldc + n;
+          *o = g.accumulate ? *o + v : v;
+        }
       } else {
         partial[((size_t)blockIdx.z * g.M + m) * g.N + n] = acc[i][j];
       }
@@ -102,6 +109,10 @@ __global__ void splitk_reduce_kernel(GemmArgs g, const float* __restrict__ parti
   for (int s = 0; s < splits; ++s) v += partial[(size_t)s * g.M * g.N + idx];
   if (g.bias) v += g.bias[n];
   const int r = g.row_deinterleave_H > 0 ? ((m & 3) * g.row_deinterleave_H + (m >> 2)) : m;
+  if (g.c_bf16) {
+    reinterpret_cast<unsigned short*>(g.c)[(long long)r * g.ldc + n] = (unsigned short)(pack_bf16x2(v, 0.f) & 0xFFFFu);
+    return;
+  }
   float* o = g.c + (long long)r * g.ldc + n;
   *o = g.accumulate ? *o + v : v;
 }
@@ -124,6 +135,7 @@ size_t gemm_simt_workspace_bytes(int M, int N, int K) {
 int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0) return 0;
   MRG_REQUIRE(g.K >= 0, "gemm: negative K");
+  MRG_REQUIRE(!(g.c_bf16 && g.accumulate), "gemm: a bfloat16 output cannot accumulate");
   const int splits = pick_splits(g.M, g.N, g.K);
   float* partial = nullptr;
   if (splits > 1) {

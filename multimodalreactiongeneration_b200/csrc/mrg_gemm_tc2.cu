@@ -72,13 +72,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t a_dst = base + s * STAGE2_BYTES;
         const uint32_t b_dst = a_dst + TILE_BYTES;
-        mbar_arrive_expect_tx(full_bar(s), 2 * TILE_BYTES);
+        mbar_arrive_expect_tx(full_bar(s), (p.a_bf16 ? TILE_BYTES / 2 : TILE_BYTES) + TILE_BYTES);
         const int k0 = (kb_begin + i) * TBK;
         if (!p.a_mn) {
-          tma_load_2d(a_dst, &tma_a, full_bar(s), k0, m0);
+          tma_load_2d(a_dst, &tma_a, full_bar(s), k0, m0);   // fp32: 128-byte rows (swizzled); bf16: 64-byte rows
         } else {
+          const uint32_t box_bytes = p.a_bf16 ? 2048u : 4096u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_2d(a_dst + j * 4096, &tma_a, full_bar(s), m0 + j * 32, k0);
+          for (int j = 0; j < 4; ++j) tma_load_2d(a_dst + j * box_bytes, &tma_a, full_bar(s), m0 + j * 32, k0);
         }
         if (!p.b_mn) {
           tma_load_2d(b_dst, &tma_b, full_bar(s), k0, n0);
@@ -109,6 +110,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           const uint64_t dbl = make_smem_desc(b_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
           if (p.single_pass) {
             umma_tf32_ts(tmem_base, ta_hi + k * 8, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          } else if (p.a_bf16) {   // A is exact in its hi part: A B = A B_lo + A B_hi
+            umma_tf32_ts(tmem_base, ta_hi + k * 8, dbl, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_ts(tmem_base, ta_hi + k * 8, dbh, idesc, 1u);
           } else {
             umma_tf32_ts(tmem_base, ta_lo + k * 8, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
             umma_tf32_ts(tmem_base, ta_hi + k * 8, dbl, idesc, 1u);
@@ -129,7 +133,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       mbar_wait(full_bar(s), ph);
       const uint8_t* at = smem_gen + s * STAGE2_BYTES;
       uint32_t hi[32], lo[32];
-      if (!p.a_mn) {
+      if (p.a_bf16) {
+        // bfloat16 tile (no swizzle): widening to fp32 is exact and fits tf32, so there is no lo part
+        if (!p.a_mn) {   // K-major: row r = 32 k x 2 bytes
+          const uint4* rp = reinterpret_cast<const uint4*>(at + row * 64);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 v = rp[c];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[c * 8 + 2 * e] = w[e] << 16;
+              hi[c * 8 + 2 * e + 1] = w[e] & 0xFFFF0000u;
+            }
+          }
+        } else {         // MN-major: four boxes of [32 k][32 m] bfloat16
+          const unsigned short* cp = reinterpret_cast<const unsigned short*>(at + (row >> 5) * 2048) + (row & 31);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) hi[k] = (uint32_t)cp[k * 32] << 16;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) lo[k] = 0u;
+      } else if (!p.a_mn) {
         // K-major tile: row r = 128 bytes, 16-byte chunk c stored at chunk (c ^ (r & 7))  [SWIZZLE_128B]
         const uint8_t* rp = at + row * 128;
 #pragma unroll
@@ -154,7 +179,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + s * 64;
       tmem_st32(taddr, hi);
-      if (!p.single_pass) tmem_st32(taddr + 32, lo);
+      if (!p.single_pass && !p.a_bf16) tmem_st32(taddr + 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -241,6 +266,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         } else {
           v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
           const int rowo = p.deint_H > 0 ? ((m & 3) * p.deint_H + (m >> 2)) : m;
+          if (p.c_bf16) {
+            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(p.c) + (long long)rowo * p.ldc + n) =
+                pack_bf16x4(v.x, v.y, v.z, v.w);
+            continue;
+          }
           float4* o = reinterpret_cast<float4*>(p.c + (long long)rowo * p.ldc + n);
           if (p.accumulate) {
             const float4 old = *o;
@@ -262,7 +292,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
 // host side ------------------------------------------------------------------------------------
 int make_tc_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k, int rows, int K, int* mn_major,
-                int a_through_tmem);
+                int a_through_tmem, int bf16);
 int tc_splits(int M, int N, int K);
 __global__ void tc_splitk_reduce_kernel(TcParams p, int splits);
 
@@ -275,8 +305,9 @@ int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStr
   }
   CUtensorMap ma, mb;
   TcParams p = {};
-  if (int e = make_tc_map(&ma, g.a, g.a_sm, g.a_sk, g.M, g.K, &p.a_mn, 1)) return e;
-  if (int e = make_tc_map(&mb, g.b, g.b_sn, g.b_sk, g.N, g.K, &p.b_mn, 0)) return e;
+  if (int e = make_tc_map(&ma, g.a, g.a_sm, g.a_sk, g.M, g.K, &p.a_mn, 1, g.a_bf16)) return e;
+  if (int e = make_tc_map(&mb, g.b, g.b_sn, g.b_sk, g.N, g.K, &p.b_mn, 0, 0)) return e;
+  p.a_bf16 = g.a_bf16; p.c_bf16 = g.c_bf16;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.kb_total = (g.K + TBK - 1) / TBK;
   const int splits = tc_splits(g.M, g.N, g.K);

@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
   const int cbase = nrows / nch, crem = nrows % nch;
   const int j0 = rank * 32;
 
-  float* gates = a.gates + (size_t)d * T * B * 4 * H;
-  const float4* gates4 = reinterpret_cast<const float4*>(gates);
+  // reserve of this direction: (i, f, g, o) in, d(pre-activations) out; 16 bytes per unit in fp32, 8 in the bf16 mode
+  const bool bf = a.bf16_gates != 0;
+  char* gates_b = reinterpret_cast<char*>(a.gates) + (size_t)d * T * B * 4 * H * (bf ? 2 : 4);
   const float* c_ext = a.c_ext + (size_t)d * (T + 1) * B * H;
 
   // ---- shared-memory state (all 12 warps) -------------------------------------------------------------------
@@ -162,7 +163,9 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
       const int t = d == 0 ? step : T - 1 - step;
       const int prev_slot = d == 0 ? t : t + 1;
       const uint32_t rj = (uint32_t)(crow0 + r) * H + j;
-      cpb_async16(smem_u32(&C.g[r][lane]), gates4 + (uint32_t)t * BH + rj);
+      if (bf) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&C.g[r][lane])),
+                           "l"(gates_b + (size_t)((uint32_t)t * BH + rj) * 8) : "memory");
+      else cpb_async16(smem_u32(&C.g[r][lane]), gates_b + (size_t)((uint32_t)t * BH + rj) * 16);
       cpb_async4(smem_u32(&C.cp[r][lane]), c_ext + (uint32_t)prev_slot * BH + rj);
       if (a.dy) cpb_async4(smem_u32(&C.dy[r][lane]), a.dy + ((uint32_t)t * B + crow0 + r) * (uint32_t)(D * H) + d * H + j);
     };
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
           const int crow0 = row0 + ch * cbase + min(ch, crem);
           // loads of this step: committed ntc groups ago (one step) by this thread
           if (ntc == 1) cpb_wait_all(); else cpb_wait_dyn(ntc - 1);
-          const float4 g = C.g[r][lane];
+          const float4 g = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.g[r][lane])) : C.g[r][lane];
           const float cprev = C.cp[r][lane];
           float dh = C.dy[r][lane];
           const float tc = fast_tanh(C.c_cur[r][lane]);
@@ -233,7 +236,11 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
           float4 db = C.db[r][lane];
           db.x += dp.x; db.y += dp.y; db.z += dp.z; db.w += dp.w;
           C.db[r][lane] = db;
-          reinterpret_cast<float4*>(gates)[(uint32_t)t * BH + (uint32_t)(crow0 + r) * H + j] = dp;
+          {
+            const size_t gidx = (size_t)((uint32_t)t * BH + (uint32_t)(crow0 + r) * H + j);
+            if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(dp.x, dp.y, dp.z, dp.w);
+            else reinterpret_cast<float4*>(gates_b)[gidx] = dp;
+          }
         }
         cpb_commit();
       }

@@ -128,10 +128,15 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, in
   const int cbase = nrows / nch, crem = nrows % nch;
   const int j0 = rank * 32;
 
-  float* gates = a.gates + (size_t)d * T * B * 4 * H;
+  // reserve of this direction: one (i, f, g, o) group per (t, row, unit): 16 bytes in fp32, 8 bytes in the bf16 mode
+  const bool bf = a.bf16_gates != 0;
+  char* gates_b = reinterpret_cast<char*>(a.gates) + (size_t)d * T * B * 4 * H * (bf ? 2 : 4);
   float* y_ext = a.y_ext + (size_t)d * (T + 1) * B * H;
   float* c_ext = a.c_ext + (size_t)d * (T + 1) * B * H;
-  const float4* gates4 = reinterpret_cast<const float4*>(gates);
+  auto fetch_xg = [&](float4* dst, uint32_t idx) {   // x-projection of (t, row, unit) -> shared memory
+    if (bf) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(gates_b + (size_t)idx * 8) : "memory");
+    else cp_async16(smem_u32(dst), gates_b + (size_t)idx * 16);
+  };
 
   // ---- initial state (all 16 warps) ---------------------------------------------------------
   const int init_slot = d == 0 ? 0 : T;
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, in
       const int crow0 = row0 + ch * cbase + min(ch, crem);
       if (r < nr) {
         C.c[r][lane] = c_ext[((size_t)init_slot * B + crow0 + r) * H + j];
-        if (T > 0) cp_async16(smem_u32(&C.xg[r][lane]), gates4 + (uint32_t)t0 * BH + (uint32_t)(crow0 + r) * H + j);
+        if (T > 0) fetch_xg(&C.xg[r][lane], (uint32_t)t0 * BH + (uint32_t)(crow0 + r) * H + j);
       }
       cp_async_commit();
     }
@@ -200,11 +205,11 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, in
         if (r < nr) {
           // x-projection of this step: committed ntc groups ago (one step) by this thread
           if (ntc == 1) cp_async_wait_all(); else cp_async_wait_dyn(ntc - 1);
-          const float4 xg = C.xg[r][lane];
+          const float4 xg = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.xg[r][lane])) : C.xg[r][lane];
           const float cold = C.c[r][lane];
           const uint32_t rj = (uint32_t)(row0 + ch * cbase + min(ch, crem) + r) * H + j;
           if (send)  // x-projection of the next step into the slot just read
-            cp_async16(smem_u32(&C.xg[r][lane]), gates4 + (uint32_t)(t + tstep) * BH + rj);
+            fetch_xg(&C.xg[r][lane], (uint32_t)(t + tstep) * BH + rj);
           REC_TRACE(10, ch, step);
           mbar_wait(smem_u32(&C.pbar), cur);  // all 8 FFMA2 warps have stored their partial sums
           REC_TRACE(11, ch, step);
@@ -243,7 +248,11 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, in
           C.c[r][lane] = cn;
           y_ext[obase + rj] = h;
           c_ext[obase + rj] = cn;
-          if (a.train) reinterpret_cast<float4*>(gates)[(uint32_t)t * BH + rj] = make_float4(gi, gf, gg, go);
+          if (a.train) {
+            const size_t gidx = (size_t)((uint32_t)t * BH + rj);
+            if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(gi, gf, gg, go);
+            else reinterpret_cast<float4*>(gates_b)[gidx] = make_float4(gi, gf, gg, go);
+          }
         }
         cp_async_commit();
       }

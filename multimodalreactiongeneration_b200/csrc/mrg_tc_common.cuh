@@ -21,6 +21,8 @@ struct TcParams {
   int deint_H;
   float* partial;       // split-K partial sums [gridDim.z][M][N] or nullptr
   int single_pass;      // MRG_F_TF32: hi*hi only
+  int a_bf16;           // A is stored as bfloat16: exact in tf32, so its lo part is zero (two passes instead of three)
+  int c_bf16;           // C is stored as bfloat16
 };
 
 // hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the low 13

@@ -42,6 +42,8 @@ def _default_flags() -> int:
         f |= _cabi.F_SIMT_GEMM
     if _PRECISION["mode"] == "tf32":
         f |= _cabi.F_TF32
+    elif _PRECISION["mode"] == "bf16":
+        f |= _cabi.F_TF32 | _cabi.F_BF16
     f |= (_BUDGET["clusters"] & 0xFF) << 16
     return f
 
@@ -73,9 +75,14 @@ def set_precision(mode: str) -> None:
     """"fp32" (default): 3xTF32 tensor-core GEMMs, fp32-grade (parity <= 1e-5 / 1e-4).
     "tf32": one tensor-core pass per GEMM (10-bit mantissa, at least bf16 precision) — the reduced
     precision mode of BASELINE.json's north_star; stated bound: states 2e-2, loss/gradients 5e-2
-    norm-relative (measured ~1e-3).  The recurrence itself is fp32 in both modes."""
-    if mode not in ("fp32", "tf32"):
-        raise ValueError("precision must be 'fp32' or 'tf32'")
+    norm-relative (measured ~1e-3).
+    "bf16": "tf32" plus bfloat16 STORAGE of the LSTM reserve — the x-projection, the saved gates and the
+    d(pre-activations) that feed the backward GEMMs are 4 x bf16 per hidden unit (8 bytes instead of 16), the GEMMs
+    next to them write / read bfloat16 directly (bf16 values are exact tf32 operands) — for the cluster kernels
+    (H in {128, 256}, T > 1); other shapes run as in "tf32".  Same stated bound: states 2e-2, loss / gradients 5e-2
+    norm-relative.  Accumulation (TMEM) and the recurrence (h W_hh, cell state, hidden states) stay fp32 in every mode."""
+    if mode not in ("fp32", "tf32", "bf16"):
+        raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
     _PRECISION["mode"] = mode
 
 
@@ -142,7 +149,9 @@ class _LSTMLayerFn(torch.autograd.Function):
         dev = x.device
         need_grad = any(ctx.needs_input_grad)
         opts = dict(dtype=torch.float32, device=dev)
-        gates = torch.empty((D, T, B, H, 4), **opts)
+        if flags & _cabi.F_BF16 and not (T > 1 and H in (128, 256) and not flags & _cabi.F_GENERIC_REC):
+            flags &= ~_cabi.F_BF16      # bf16 reserve: cluster kernels only; other shapes keep the fp32 reserve
+        gates = torch.empty((D, T, B, H, 4), dtype=torch.bfloat16 if flags & _cabi.F_BF16 else torch.float32, device=dev)
         y_ext = torch.empty((D, T + 1, B, H), **opts)
         c_ext = torch.empty((D, T + 1, B, H), **opts)
         w_pack = torch.empty((D, 4 * H, I), **opts)
