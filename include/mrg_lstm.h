@@ -97,8 +97,10 @@ int mrg_device_info(int* sm_count, int* max_clusters_h256, int* max_clusters_h12
 size_t mrg_lstm_workspace_bytes(int T, int B, int I, int H, int D);
 
 /* One nn.LSTM layer, D = 1 (uni) or 2 (bidirectional) directions in one launch.
- * w_pack: caller-owned buffer of D*4H*I floats; receives W_ih with gate-interleaved rows and is
- * consumed again by the backward. */
+ * w_pack: caller-owned buffer of mrg_lstm_pack_floats(I, H, D) = 3*D*4H*I floats; receives W_ih with gate-interleaved
+ * rows in three planes — as is, its tf32 hi part, its lo part — (the B operand of the projection and dX GEMMs, split
+ * once per forward instead of once per tile) and is consumed again by the backward. */
+size_t mrg_lstm_pack_floats(int I, int H, int D);
 int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights* w, float* w_pack, float* gates,
                            float* y_ext, float* c_ext, void* workspace, size_t workspace_bytes, int T,
                            int B, int I, int H, int D, int flags, void* stream);
@@ -124,6 +126,18 @@ int mrg_gemm_strided(const float* a, long long a_sm, long long a_sk, const float
                      int accumulate, int deint_H, void* workspace, size_t workspace_bytes, int flags,
                      void* stream);
 size_t mrg_gemm_workspace_bytes(int M, int N, int K);
+
+/* Weight operand split once: hi[i] = w[i] rounded to tf32 (nearest, ties away), lo[i] = w[i] - hi[i] (exact).
+ * mrg_gemm_strided_split is mrg_gemm_strided (no de-interleave) with B given as those two planes: it runs the persistent
+ * 128 x 256 tcgen05 kernel (csrc/mrg_gemm_tc4.cu), which needs no B conversion pass.  Covered shapes:
+ * mrg_gemm_split_supported() != 0 (N > 128, strides as for mrg_gemm_strided, 16-byte aligned pointers); it fails loudly
+ * otherwise — the caller falls back to mrg_gemm_strided with the unsplit weight. */
+int mrg_split_tf32(const float* w, float* hi, float* lo, size_t n, void* stream);
+int mrg_gemm_split_supported(int M, int N, int K, long long a_sm, long long a_sk, long long b_sk, long long b_sn,
+                             long long ldc);
+int mrg_gemm_strided_split(const float* a, long long a_sm, long long a_sk, const float* b_hi, const float* b_lo,
+                           long long b_sk, long long b_sn, const float* bias, float* c, long long ldc, int M, int N,
+                           int K, int accumulate, void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* Fused residual + LayerNorm — ResidualConnection.forward, mr_gen/model/utils/residual_connection.py:29-32:
  * out = LN(y + x) * gamma + beta over the last dimension (H in {128, 256, 512}).  Rows are indexed (i0, i1),

@@ -21,6 +21,7 @@ EXPORTS = (
     "mrg_residual_layernorm_backward", "mrg_adamw_flat", "mrg_debug_set_trace", "mrg_colsum", "mrg_colsum_workspace_bytes",
     "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
     "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward", "mrg_profile_kernel_name",
+    "mrg_lstm_pack_floats", "mrg_split_tf32", "mrg_gemm_split_supported", "mrg_gemm_strided_split",
 )
 
 
@@ -94,6 +95,15 @@ def lib() -> ctypes.CDLL:
     L.mrg_gemm_strided.argtypes = [c_void_p, LL, LL, c_void_p, LL, LL, c_void_p, c_void_p, LL, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]
     L.mrg_gemm_strided.restype = c_int
+    L.mrg_lstm_pack_floats.argtypes = [c_int, c_int, c_int]
+    L.mrg_lstm_pack_floats.restype = c_size_t
+    L.mrg_split_tf32.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.mrg_split_tf32.restype = c_int
+    L.mrg_gemm_split_supported.argtypes = [c_int, c_int, c_int, LL, LL, LL, LL, LL]
+    L.mrg_gemm_split_supported.restype = c_int
+    L.mrg_gemm_strided_split.argtypes = [c_void_p, LL, LL, c_void_p, c_void_p, LL, LL, c_void_p, c_void_p, LL, c_int,
+                                         c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]
+    L.mrg_gemm_strided_split.restype = c_int
     L.mrg_gemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.mrg_gemm_workspace_bytes.restype = c_size_t
     L.mrg_layernorm_workspace_bytes.argtypes = [c_int]

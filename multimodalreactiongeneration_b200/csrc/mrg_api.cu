@@ -7,6 +7,8 @@
 
 namespace mrg {
 int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int gemm_tc4(const GemmArgs& g, cudaStream_t stream);
+bool gemm_tc4_supported(const GemmArgs& g);
 bool gemm_tc_supported(const GemmArgs& g);
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 
@@ -15,6 +17,12 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int run_gemm(const GemmArgs& g_in, void* ws, size_t ws_bytes, int flags, cudaStream_t stream) {
   GemmArgs g = g_in;
   g.single_pass = (flags & (MRG_F_TF32 | MRG_F_BF16)) ? 1 : 0;
+  static int no_tc4 = -1;
+  if (no_tc4 < 0) {
+    const char* e = getenv("MRG_NO_TC4");   // developer switch: keep the 128 x 128 kernel for every GEMM
+    no_tc4 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!(flags & MRG_F_SIMT_GEMM) && !no_tc4 && g.K > 0 && gemm_tc4_supported(g)) return gemm_tc4(g, stream);
   if (!(flags & MRG_F_SIMT_GEMM) && gemm_tc_supported(g)) return gemm_tc2(g, ws, ws_bytes, stream);
   return gemm_simt(g, ws, ws_bytes, stream);
 }
@@ -127,6 +135,7 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     GemmArgs g = {};
     g.a = x; g.a_sm = I; g.a_sk = 1;
     g.b = w_pack + (size_t)d * 4 * H * I; g.b_sk = 1; g.b_sn = I;
+    g.b_hi = g.b + (size_t)D * 4 * H * I; g.b_lo = g.b_hi + (size_t)D * 4 * H * I;
     g.bias = bias_pack + (size_t)d * 4 * H;
     // bf16 mode: the reserve is bfloat16, direction d starts half as many bytes in
     g.c = bf16 ? reinterpret_cast<float*>(reinterpret_cast<unsigned short*>(gates) + (size_t)d * T * B * 4 * H)
@@ -248,6 +257,7 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
       GemmArgs m = {};
       m.a = dpre; m.a_sm = 4 * H; m.a_sk = 1;
       m.b = w_pack + (size_t)d * 4 * H * I; m.b_sk = I; m.b_sn = 1;
+      m.b_hi = m.b + (size_t)D * 4 * H * I; m.b_lo = m.b_hi + (size_t)D * 4 * H * I;
       m.c = dx; m.ldc = I;
       m.M = T * B; m.N = I; m.K = 4 * H;
       m.accumulate = d > 0 ? 1 : 0; m.a_bf16 = bf16 ? 1 : 0;
@@ -283,5 +293,39 @@ extern "C" int mrg_gemm_strided(const float* a, long long a_sm, long long a_sk, 
   g.accumulate = accumulate; g.row_deinterleave_H = deint_H;
   return run_gemm(g, workspace, workspace_bytes, flags, (cudaStream_t)stream);
 }
+
+extern "C" int mrg_gemm_strided_split(const float* a, long long a_sm, long long a_sk, const float* b_hi,
+                                      const float* b_lo, long long b_sk, long long b_sn, const float* bias, float* c,
+                                      long long ldc, int M, int N, int K, int accumulate, void* workspace,
+                                      size_t workspace_bytes, int flags, void* stream) {
+  MRG_REQUIRE(a && b_hi && b_lo && c && M >= 0 && N >= 0 && K >= 0, "mrg_gemm_strided_split: bad arguments");
+  MRG_REQUIRE(check_device() == 1, "mrg_gemm_strided_split: this library only runs on compute capability 10.x (B200)");
+  GemmArgs g = {};
+  g.a = a; g.a_sm = a_sm; g.a_sk = a_sk;
+  g.b_hi = b_hi; g.b_lo = b_lo; g.b_sk = b_sk; g.b_sn = b_sn;
+  g.b = b_hi;   // operand checks of the tensor-core path look at b
+  g.bias = bias; g.c = c; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K;
+  g.accumulate = accumulate;
+  g.single_pass = (flags & (MRG_F_TF32 | MRG_F_BF16)) ? 1 : 0;
+  MRG_REQUIRE(!(flags & MRG_F_SIMT_GEMM) && g.K > 0 && gemm_tc4_supported(g),
+              "mrg_gemm_strided_split: shape / alignment not covered by the pre-split kernel (see mrg_gemm_split_supported)");
+  (void)workspace; (void)workspace_bytes;
+  return gemm_tc4(g, (cudaStream_t)stream);
+}
+
+extern "C" int mrg_gemm_split_supported(int M, int N, int K, long long a_sm, long long a_sk, long long b_sk,
+                                        long long b_sn, long long ldc) {
+  // alignment of the pointers is the caller's (16 bytes); this checks the shape and stride rules
+  if (M < 4096 || K <= 0 || N <= 128 || N % 4 != 0 || ldc % 4 != 0) return 0;
+  auto ok = [](long long s_r, long long s_k) {
+    if (s_k == 1) return s_r >= 4 && s_r % 4 == 0;
+    if (s_r == 1) return s_k >= 4 && s_k % 4 == 0;
+    return false;
+  };
+  return ok(a_sm, a_sk) && ok(b_sn, b_sk) ? 1 : 0;
+}
+
+extern "C" size_t mrg_lstm_pack_floats(int I, int H, int D) { return (size_t)3 * D * 4 * H * I; }
 
 extern "C" size_t mrg_gemm_workspace_bytes(int M, int N, int K) { return gemm_ws(M, N, K) + 256; }

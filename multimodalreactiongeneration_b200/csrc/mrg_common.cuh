@@ -242,6 +242,8 @@ struct GemmArgs {
   int single_pass;         // tensor-core path only: one tf32 pass (MRG_F_TF32) instead of 3xTF32
   int a_bf16;              // bf16 mode: the A operand is stored as bfloat16 (a points to uint16 data, strides in elements)
   int c_bf16;              // bf16 mode: C is stored as bfloat16 (round to nearest even); no accumulate, no de-interleave
+  const float* b_hi;       // optional: B already split into tf32 hi / lo planes (same strides as b; weights, split once
+  const float* b_lo;       // per step by pack_kernel / mrg_split_tf32) -> the persistent 128 x 256 kernel (mrg_gemm_tc4.cu)
 };
 
 // bfloat16 storage helpers of the bf16 mode (the reserve of the recurrent kernels and the GEMM operands next to it)
@@ -259,9 +261,16 @@ __device__ __forceinline__ float4 unpack_bf16x4(uint2 v) {
   return make_float4(bf16_lo_to_f32(v.x), bf16_hi_to_f32(v.x), bf16_lo_to_f32(v.y), bf16_hi_to_f32(v.y));
 }
 
+// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the low 13
+// bits) with two full-rate integer ops instead of cvt.rna.tf32.f32 (a quarter-rate conversion-pipe op).
+// lo = x - hi is exact in fp32 and is handed to the tensor core as is: it ignores the low 13 mantissa
+// bits of a tf32 operand, an error of 2^-10 relative to lo, i.e. 2^-21 relative to x.
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
 int gemm_simt(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t gemm_simt_workspace_bytes(int M, int N, int K);
 
+// w_pack: three planes of [D][4H][I] floats — gate-interleaved W_ih as is, its tf32 hi part, its lo part (x - hi)
 int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, float* whh_pack, int I, int H,
                  int D, cudaStream_t stream);
 

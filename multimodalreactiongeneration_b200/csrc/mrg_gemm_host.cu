@@ -49,10 +49,11 @@ static EncodeTiledFn get_encode_fn() {
 // operand X(r, k): element (r,k) at ptr[r*s_r + k*s_k]; K-major if s_k == 1, MN-major if s_r == 1
 // `plain_mn`: an MN-major operand that is read element-wise by converter threads (the TMEM-operand kernel) is
 // loaded without swizzle (box = 32 rows x 32 k, 4 boxes per tile).
+// `box_rows`: rows of a K-major tile (128, or 256 for the B operand of the 128 x 256 kernel).
 // `bf16`: the operand is stored as bfloat16 (only for an A operand that goes through the converter warps: plain tiles,
 // 64-byte rows, no swizzle).
 int make_tc_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k, int rows, int K, int* mn_major,
-                int plain_mn, int bf16) {
+                int plain_mn, int bf16, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return MRG_E_UNSUPPORTED; }
   cuuint64_t dims[2], strides[1];
@@ -62,7 +63,7 @@ int make_tc_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k
     *mn_major = 0;
     dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
     strides[0] = (cuuint64_t)s_r * esz;
-    box[0] = TBK; box[1] = TBM;
+    box[0] = TBK; box[1] = (cuuint32_t)box_rows;
   } else {                  // MN-major: inner = rows
     *mn_major = 1;
     dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;

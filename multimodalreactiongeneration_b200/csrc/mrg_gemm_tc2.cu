@@ -18,6 +18,20 @@
 
 namespace mrg {
 
+#ifdef MRG_REC_TRACE
+#define GEMM_TRACE_DECL unsigned trace_n = 0; const bool trace_cta = p.trace && blockIdx.x == 0 && blockIdx.z == 0 && blockIdx.y == gridDim.y / 2;
+#define GEMM_TRACE(evt, i)                                                                                  \
+  if (trace_cta && (threadIdx.x & 31) == 0 && trace_n < 1024u) {                                            \
+    unsigned long long* tp = p.trace + ((size_t)(threadIdx.x >> 5) * 1024 + trace_n) * 2;                   \
+    tp[0] = clock64();                                                                                      \
+    tp[1] = ((unsigned long long)(threadIdx.x >> 5) << 48) | ((unsigned long long)(evt) << 32) | (unsigned long long)(i); \
+    ++trace_n;                                                                                              \
+  }
+#else
+#define GEMM_TRACE_DECL
+#define GEMM_TRACE(evt, i)
+#endif
+
 constexpr int STAGE2_BYTES = 3 * TILE_BYTES;                // A raw, B_hi, B_lo
 // S2 = pipeline stages: 4 with one CTA per SM (long K), or 2 with TWO co-resident CTAs per SM (short K: one CTA's
 // prologue / epilogue overlaps the other's main loop; 2 x (128 accumulator + 2 x 64 operand) TMEM columns)
@@ -44,6 +58,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
   const int nkb = max(0, kb_end - kb_begin);
+  GEMM_TRACE_DECL
+  GEMM_TRACE(1, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S2; ++s) {
@@ -63,6 +79,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+  GEMM_TRACE(2, 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -70,6 +87,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S2, ph = (i / S2) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
+        GEMM_TRACE(10, i);
         const uint32_t a_dst = base + s * STAGE2_BYTES;
         const uint32_t b_dst = a_dst + TILE_BYTES;
         mbar_arrive_expect_tx(full_bar(s), (p.a_bf16 ? TILE_BYTES / 2 : TILE_BYTES) + TILE_BYTES);
@@ -101,6 +119,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S2, ph = (i / S2) & 1;
         mbar_wait(cvt_bar(s), ph);
+        GEMM_TRACE(20, i);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t b_hi = base + s * STAGE2_BYTES + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
         const uint32_t ta_hi = tmem_base + ACC_COLS + s * 64, ta_lo = ta_hi + 32;
@@ -120,6 +139,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           }
         }
         umma_commit(empty_bar(s));
+        GEMM_TRACE(21, i);
       }
       umma_commit(acc_bar);
     }
@@ -131,6 +151,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     for (int i = 0; i < nkb; ++i) {
       const int s = i % S2, ph = (i / S2) & 1;
       mbar_wait(full_bar(s), ph);
+      GEMM_TRACE(30, i);
       const uint8_t* at = smem_gen + s * STAGE2_BYTES;
       uint32_t hi[32], lo[32];
       if (p.a_bf16) {
@@ -184,6 +205,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(cvt_bar(s));
+      GEMM_TRACE(31, i);
     }
   } else if (warp >= 8) {
     // ===================== B converter: raw tile -> hi (in place) / lo tiles in shared memory ===========
@@ -191,6 +213,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     for (int i = 0; i < nkb; ++i) {
       const int s = i % S2, ph = (i / S2) & 1;
       mbar_wait(full_bar(s), ph);
+      GEMM_TRACE(40, i);
       float4* hi = reinterpret_cast<float4*>(smem_gen + s * STAGE2_BYTES + TILE_BYTES);
       float4* lo = reinterpret_cast<float4*>(smem_gen + s * STAGE2_BYTES + 2 * TILE_BYTES);
 #pragma unroll
@@ -209,6 +232,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(cvt_bar(s));
+      GEMM_TRACE(41, i);
     }
   }
 
@@ -219,10 +243,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int q = warp & 3;
     const int half = warp >> 2;
     __syncwarp();
+    GEMM_TRACE(50, 0);
     if (nkb > 0) {
       mbar_wait(acc_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    GEMM_TRACE(51, 0);
 #pragma unroll 1
     for (int cc = 0; cc < (half < 2 ? 2 : 0); ++cc) {
       uint32_t r[32];
@@ -252,6 +278,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    GEMM_TRACE(52, 0);
     const int n = n0 + lane * 4;
     if (n < p.N) {
       float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -281,6 +308,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       }
     }
   }
+  GEMM_TRACE(53, 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
@@ -292,7 +320,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
 // host side ------------------------------------------------------------------------------------
 int make_tc_map(CUtensorMap* map, const float* ptr, long long s_r, long long s_k, int rows, int K, int* mn_major,
-                int a_through_tmem, int bf16);
+                int a_through_tmem, int bf16, int box_rows);
 int tc_splits(int M, int N, int K);
 __global__ void tc_splitk_reduce_kernel(TcParams p, int splits);
 
@@ -305,8 +333,8 @@ int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStr
   }
   CUtensorMap ma, mb;
   TcParams p = {};
-  if (int e = make_tc_map(&ma, g.a, g.a_sm, g.a_sk, g.M, g.K, &p.a_mn, 1, g.a_bf16)) return e;
-  if (int e = make_tc_map(&mb, g.b, g.b_sn, g.b_sk, g.N, g.K, &p.b_mn, 0, 0)) return e;
+  if (int e = make_tc_map(&ma, g.a, g.a_sm, g.a_sk, g.M, g.K, &p.a_mn, 1, g.a_bf16, TBM)) return e;
+  if (int e = make_tc_map(&mb, g.b, g.b_sn, g.b_sk, g.N, g.K, &p.b_mn, 0, 0, TBN)) return e;
   p.a_bf16 = g.a_bf16; p.c_bf16 = g.c_bf16;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.kb_total = (g.K + TBK - 1) / TBK;
@@ -316,6 +344,7 @@ int gemm_tc2(const GemmArgs& g, void* workspace, size_t workspace_bytes, cudaStr
   p.c = g.c; p.ldc = g.ldc; p.bias = g.bias; p.accumulate = g.accumulate; p.deint_H = g.row_deinterleave_H;
   p.partial = nullptr;
   p.single_pass = g.single_pass;
+  p.trace = debug_trace_buffer();
   if (zdim > 1) {
     const size_t need = (size_t)zdim * g.M * g.N * sizeof(float);
     if (workspace == nullptr || workspace_bytes < need) {

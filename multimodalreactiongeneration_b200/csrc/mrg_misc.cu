@@ -59,7 +59,14 @@ __global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __res
   const int j = row >> 2, g = row & 3;
   const float* src = p.w_ih[d] + (size_t)(g * H + j) * I;
   float* dst = w_pack + ((size_t)d * 4 * H + row) * I;
-  for (int i = threadIdx.x; i < I; i += blockDim.x) dst[i] = src[i];
+  const size_t plane = (size_t)gridDim.y * 4 * H * I;   // raw | tf32 hi | lo planes (B operand of mrg_gemm_tc4.cu)
+  for (int i = threadIdx.x; i < I; i += blockDim.x) {
+    const float v = src[i];
+    const float hi = __uint_as_float(tf32_rna(v));
+    dst[i] = v;
+    dst[plane + i] = hi;
+    dst[2 * plane + i] = v - hi;
+  }
   if (whh_pack != nullptr) {  // single-step path: h0 * W_hh^T is a second projection GEMM
     const float* hs = p.w_hh[d] + (size_t)(g * H + j) * H;
     float* hd = whh_pack + ((size_t)d * 4 * H + row) * H;
@@ -88,6 +95,28 @@ int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack,
   count_launch();
   return 0;
 }
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const float h = __uint_as_float(tf32_rna(v));
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+}  // namespace mrg
+extern "C" int mrg_split_tf32(const float* w, float* hi, float* lo, size_t n, void* stream) {
+  MRG_REQUIRE(w && hi && lo, "mrg_split_tf32: null pointer");
+  if (n == 0) return 0;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  mrg::split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  mrg::count_launch();
+  return 0;
+}
+namespace mrg {
 
 // db[g*H+j] (+)= sum_b part[b][j][g]
 __global__ void colsum_kernel(const float* __restrict__ part, float* __restrict__ db, int B, int H,

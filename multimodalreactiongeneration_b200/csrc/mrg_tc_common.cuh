@@ -23,13 +23,9 @@ struct TcParams {
   int single_pass;      // MRG_F_TF32: hi*hi only
   int a_bf16;           // A is stored as bfloat16: exact in tf32, so its lo part is zero (two passes instead of three)
   int c_bf16;           // C is stored as bfloat16
+  unsigned long long* trace;  // developer event trace (-DMRG_REC_TRACE builds), else nullptr
 };
 
-// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the low 13
-// bits) with two full-rate integer ops instead of cvt.rna.tf32.f32 (a quarter-rate conversion-pipe op).
-// lo = x - hi is exact in fp32 and is handed to the tensor core as is: it ignores the low 13 mantissa
-// bits of a tf32 operand, an error of 2^-10 relative to lo, i.e. 2^-21 relative to x.
-__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(

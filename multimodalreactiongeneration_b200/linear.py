@@ -25,6 +25,35 @@ def _gemm(a, a_sm, a_sk, b, b_sk, b_sn, bias, c, M, N, K, flags, accumulate=0):
     _cabi.check(st, "mrg_gemm_strided")
 
 
+def _split_ok(M, N, K, a_sm, a_sk, b_sk, b_sn, flags):
+    """Does the persistent pre-split-weight kernel (csrc/mrg_gemm_tc4.cu) cover this GEMM?"""
+    if flags & _cabi.F_SIMT_GEMM:
+        return False
+    return bool(_cabi.lib().mrg_gemm_split_supported(M, N, K, a_sm, a_sk, b_sk, b_sn, N))
+
+
+def _split_weight(w):
+    """[2, *w.shape]: tf32 hi part and lo = w - hi of a weight matrix (one small launch per forward; the planes are
+    reused by the backward's dX GEMM)."""
+    L = _cabi.lib()
+    hl = torch.empty((2,) + tuple(w.shape), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        st = L.mrg_split_tf32(w.data_ptr(), hl[0].data_ptr(), hl[1].data_ptr(), w.numel(),
+                              torch.cuda.current_stream(w.device).cuda_stream)
+    _cabi.check(st, "mrg_split_tf32")
+    return hl
+
+
+def _gemm_split(a, a_sm, a_sk, hl, b_sk, b_sn, bias, c, M, N, K, flags):
+    L = _cabi.lib()
+    dev = c.device
+    with torch.cuda.device(dev):
+        st = L.mrg_gemm_strided_split(a.data_ptr(), a_sm, a_sk, hl[0].data_ptr(), hl[1].data_ptr(), b_sk, b_sn,
+                                      _cabi.ptr(bias), c.data_ptr(), N, M, N, K, 0, None, 0, flags,
+                                      torch.cuda.current_stream(dev).cuda_stream)
+    _cabi.check(st, "mrg_gemm_strided_split")
+
+
 def _colsum(x2, into=None):
     """Column sums of a contiguous [M, N] fp32 matrix (bias gradient) through the C-ABI (``mrg_colsum``).
     ``into``: accumulate into this [N] tensor instead of returning a new one."""
@@ -66,8 +95,16 @@ class _LinearFn(torch.autograd.Function):
         M = x2.shape[0]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         flags = _default_flags()
-        if M > 0:
-            _gemm(x2, K, 1, weight.contiguous(), 1, K, bias, y, M, N, K, flags)
+        w = weight.contiguous()
+        aligned = w.data_ptr() % 16 == 0 and x2.data_ptr() % 16 == 0 and (bias is None or bias.data_ptr() % 16 == 0)
+        fwd_split = aligned and M > 0 and _split_ok(M, N, K, K, 1, 1, K, flags)
+        bwd_split = aligned and M > 0 and ctx.needs_input_grad[0] and _split_ok(M, K, N, N, 1, K, 1, flags)
+        hl = _split_weight(w) if (fwd_split or bwd_split) else None
+        if fwd_split:
+            _gemm_split(x2, K, 1, hl, 1, K, bias, y, M, N, K, flags)
+        elif M > 0:
+            _gemm(x2, K, 1, w, 1, K, bias, y, M, N, K, flags)
+        ctx.split = hl if bwd_split else None
         ctx.save_for_backward(x2, weight)
         ctx.params = (weight, bias)   # the python objects (saved_tensors may hand back fresh wrappers)
         ctx.has_bias = bias is not None
@@ -84,7 +121,9 @@ class _LinearFn(torch.autograd.Function):
         w = weight.contiguous()
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-            if M > 0:   # dx[M,K] = dy[M,N] · W[N,K]
+            if M > 0 and ctx.split is not None and dy2.data_ptr() % 16 == 0:   # dx[M,K] = dy[M,N] · W[N,K]
+                _gemm_split(dy2, N, 1, ctx.split, K, 1, None, dx, M, K, N, ctx.flags)
+            elif M > 0:
                 _gemm(dy2, N, 1, w, K, 1, None, dx, M, K, N, ctx.flags)
             dx = dx.view(*dy.shape[:-1], K)
         wp, bp = ctx.params

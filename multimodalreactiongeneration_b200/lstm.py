@@ -154,7 +154,7 @@ class _LSTMLayerFn(torch.autograd.Function):
         gates = torch.empty((D, T, B, H, 4), dtype=torch.bfloat16 if flags & _cabi.F_BF16 else torch.float32, device=dev)
         y_ext = torch.empty((D, T + 1, B, H), **opts)
         c_ext = torch.empty((D, T + 1, B, H), **opts)
-        w_pack = torch.empty((D, 4 * H, I), **opts)
+        w_pack = torch.empty((L.mrg_lstm_pack_floats(I, H, D),), **opts)   # W_ih: raw | tf32 hi | lo planes
         nbytes = L.mrg_lstm_workspace_bytes(T, B, I, H, D)
         ws = _workspace(dev, nbytes)
         dw = (_cabi.DirWeights * D)()
