@@ -266,6 +266,18 @@ int mrg_gru_forward(const float* gx, const float* w_hh, const float* w_hh_t, con
 int mrg_gru_backward(const float* dy, const float* dh_n, const float* reserve, const float* y_ext, const float* w_hh,
                      float* dgx, float* dgh, float* dh0, int T, int B, int H, void* stream);
 
+/* On-GPU audio feature front-end: what AudioPreprocessor.__call__ computes after reading the
+ * waveform — mr_gen/utils/preprocess/audio.py:30-37 (log-mel + log-power, 27-d at the reference's 26 mels) and :55-67
+ * (delta / delta-delta by first differences -> 81-d).  The windowed real DFT is a GEMM of this library (mrg_gemm_strided
+ * over the waveform viewed as overlapping frames, row stride = hop) and is the caller's; this call turns its output into
+ * features.  spec: [rows][ld_spec] with re of bin k at column k and im at column bins + k (bins = nfft/2 + 1); frame j of
+ * sequence b is row b * frame_stride + j and starts at sample b * samples_per_seq + j * hop of `wave`.  mel_fb
+ * [bins][nmels] (torchaudio.functional.melscale_fbanks layout).  feat [B][frames_per_seq][nmels + 1] is scratch (the
+ * static features); out [B][frames_per_seq - delta_order][(nmels + 1) * (delta_order + 1)]. */
+int mrg_audio_features(const float* spec, int ld_spec, const float* wave, const float* mel_fb, float* feat, float* out,
+                       int B, int frames_per_seq, long long frame_stride, long long samples_per_seq, int hop, int nfft,
+                       int nmels, int delta_order, void* stream);
+
 /* Developer hook: device buffer of 16*1024*2 uint64 that -DMRG_REC_TRACE builds of the recurrent kernels fill
  * with (clock, event) records; NULL disables.  No effect in regular builds. */
 int mrg_debug_set_trace(unsigned long long* buf);

@@ -22,6 +22,7 @@ EXPORTS = (
     "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
     "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward", "mrg_profile_kernel_name",
     "mrg_lstm_pack_floats", "mrg_split_tf32", "mrg_gemm_split_supported", "mrg_gemm_strided_split",
+    "mrg_audio_features",
 )
 
 
@@ -104,6 +105,9 @@ def lib() -> ctypes.CDLL:
     L.mrg_gemm_strided_split.argtypes = [c_void_p, LL, LL, c_void_p, c_void_p, LL, LL, c_void_p, c_void_p, LL, c_int,
                                          c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]
     L.mrg_gemm_strided_split.restype = c_int
+    L.mrg_audio_features.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, LL, LL, c_int,
+                                     c_int, c_int, c_int, c_void_p]
+    L.mrg_audio_features.restype = c_int
     L.mrg_gemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.mrg_gemm_workspace_bytes.restype = c_size_t
     L.mrg_layernorm_workspace_bytes.argtypes = [c_int]

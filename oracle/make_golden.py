@@ -155,10 +155,51 @@ def gru_mixer_fixture(ns):
           {**{k: p.grad for k, p in m.named_parameters()}, "x": x.grad}, {"hx_is_none": hx is None})
 
 
+def audio_fixture():
+    """AudioPreprocessor of the reference (mr_gen/utils/preprocess/audio.py) on a seeded waveform.  The class is loaded
+    from its own file; the only stub is ``torchaudio._backend.soundfile_backend`` (absent from this torchaudio; it is
+    the file reader, which is bypassed: the steps of ``__call__`` after the read are executed here verbatim)."""
+    import importlib.util
+    import sys
+    import types
+    from oracle.ref_loader import REFERENCE_ROOT
+    if "torchaudio._backend.soundfile_backend" not in sys.modules:
+        be = types.ModuleType("torchaudio._backend")
+        sf = types.ModuleType("torchaudio._backend.soundfile_backend")
+        be.soundfile_backend = sf
+        sys.modules["torchaudio._backend"] = be
+        sys.modules["torchaudio._backend.soundfile_backend"] = sf
+    spec = importlib.util.spec_from_file_location(
+        "_ref_audio", os.path.join(REFERENCE_ROOT, "mr_gen", "utils", "preprocess", "audio.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = types.SimpleNamespace(nfft=400, shift=160, nmels=26, sample_rate=16000, delta_order=2)
+    g = torch.Generator().manual_seed(77)
+    n = 16000 + 240                                   # one second and a bit: 100 frames -> 98 after the deltas
+    t = torch.arange(n) / 16000.0
+    wave = 0.3 * torch.sin(2 * torch.pi * 220.0 * t) + 0.1 * torch.sin(2 * torch.pi * 3100.0 * t) \
+        + 0.05 * torch.randn(n, generator=g)
+    wave[4000:5200] = 0.0                             # a silent stretch: the 1e-6 / 1e-10 clamps are exercised
+    blob = {"in/wave": wave.numpy()}
+    for order in (0, 1, 2):
+        cfg.delta_order = order
+        pre = mod.AudioPreprocessor(cfg)
+        fbank = pre.fbank(wave)                       # audio.py:30-37, verbatim
+        fbank = pre.log(torch.clamp(fbank, 1e-10))
+        power = pre.compute_log_power(wave)
+        fbank = torch.cat([fbank, power.unsqueeze(0)], dim=0).T.to(torch.float32)
+        blob[f"out/features_order{order}"] = pre.compute_delta(fbank).numpy()
+    path = os.path.join(OUT, "audio_features.npz")
+    np.savez_compressed(path, **blob)
+    print(f"audio_features: {os.path.getsize(path) / 1024:.0f} KB")
+
+
 def main():
     import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
+    if "--only-audio" in sys.argv:
+        return audio_fixture()
     ns = load_reference()
     if "--only-metaformer" in sys.argv:
         return metaformer_fixture(ns)
@@ -279,6 +320,7 @@ def main():
 
     metaformer_fixture(ns)
     gru_mixer_fixture(ns)
+    audio_fixture()
 
 
 if __name__ == "__main__":

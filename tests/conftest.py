@@ -35,6 +35,11 @@ def load_golden(name):
     return parts["sd"], parts["in"], parts["out"], parts["grad"], parts["meta"]
 
 
+def golden(name):
+    """The raw npz of a fixture (numpy arrays keyed "in/..", "out/..")."""
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
 def rel_err(a, b):
     """norm-relative error  ||a-b||_inf / ||b||_inf  (SURVEY.md §8c recommended metric)."""
     a, b = a.detach().double(), b.detach().double()

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import golden, load_golden, rel_err
 from oracle import lstm_numpy, philox, ref_port
 
 
@@ -171,3 +171,25 @@ def test_numpy_gru_matches_torch_forward_and_autograd():
     for got, ref in zip(grads, (x.grad, m.weight_ih_l0.grad, m.weight_hh_l0.grad, m.bias_ih_l0.grad,
                                 m.bias_hh_l0.grad, h0.grad[0])):
         assert np.abs(got - n(ref)).max() < 1e-10
+
+
+def test_audio_oracle_matches_reference_fixture_and_product_filterbank():
+    """oracle/audio_ref.py (fp64 numpy) against the output of the reference's AudioPreprocessor (fixture made by
+    oracle/make_golden.py from the unmodified class); the product's mel filterbank / DFT basis (host constants of the GPU
+    front-end) against the oracle's filterbank and numpy's rfft."""
+    from oracle.audio_ref import audio_features, mel_filterbank
+    from multimodalreactiongeneration_b200.mr_gen.utils.preprocess import audio as fe
+    d = golden("audio_features")
+    for order in (0, 1, 2):
+        ref = d[f"out/features_order{order}"]
+        mine = audio_features(d["in/wave"], 400, 160, 26, 16000, order)
+        assert mine.shape == ref.shape
+        assert np.abs(mine - ref).max() <= 5e-5
+    assert np.abs(fe.mel_filterbank(201, 26, 16000) - mel_filterbank(201, 26, 16000)).max() <= 1e-12
+    basis = fe.dft_basis(400, 404)
+    x = np.random.default_rng(0).standard_normal(400)
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(400) / 400)
+    spec = np.fft.rfft(x * w)
+    assert np.abs(basis[:201] @ x - spec.real).max() <= 1e-9
+    assert np.abs(basis[201:402] @ x - spec.imag).max() <= 1e-9
+    assert np.abs(basis[402:]).max() == 0.0
