@@ -59,6 +59,11 @@ extern "C" {
                                   the largest buffer of the path; the GEMMs around it take / write bfloat16 and run one
                                   tf32 tensor-core pass (bf16 values are exact in tf32), accumulation and the
                                   recurrence stay fp32.  Cluster kernels only: H in {128, 256}, T > 1               */
+#define MRG_F_GRU        128   /* the layer is a GRU run on the LSTM machinery (nn.GRU at mixer_block.py:194): the caller passes
+                                  the weights in four-gate form — w_ih rows (r, z, n, 0), w_hh rows (r, z, 0, n), b_ih =
+                                  (b_ir + b_hr, b_iz + b_hz, b_in, b_hn), b_hh = NULL — the recurrent kernels apply the
+                                  GRU cell, the reserve holds (r, z, n, W_hn h + b_hn) and comes back as (d r_pre, d z_pre,
+                                  d n_pre, d n_pre r); c_ext / c0 / dc_n are unused.  H in {128, 256}, T > 1            */
 #define MRG_F_CLUSTER_BUDGET(n) (((n) & 0xFF) << 16)  /* recurrent kernels use at most n clusters (0 = all): lets two
                                   independent LSTM stacks (audio / motion encoders) run side by side on two streams */
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that

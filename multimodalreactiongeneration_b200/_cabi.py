@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libmrg_b200.so")
 F_TRAIN, F_GENERIC_REC, F_SIMT_GEMM, F_ACCUMULATE, F_ZERO_STATE, F_TF32 = 1, 2, 4, 8, 16, 32
 F_ACC_WEIGHTS = 256
 F_BF16 = 64
+F_GRU = 128
 F_BWD_NO_WGRAD, F_BWD_WGRAD_ONLY = 2048, 4096
 
 EXPORTS = (

@@ -105,6 +105,9 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   const bool bf16 = (flags & MRG_F_BF16) != 0;
   MRG_REQUIRE(!bf16 || (T > 1 && rec2_supported(H) && !(flags & MRG_F_GENERIC_REC)),
               "mrg_lstm_layer_forward: MRG_F_BF16 needs the cluster kernels (H in {128, 256}, T > 1)");
+  const bool gru = (flags & MRG_F_GRU) != 0;
+  MRG_REQUIRE(!gru || (T > 1 && rec2_supported(H) && !(flags & MRG_F_GENERIC_REC)),
+              "mrg_lstm_layer_forward: MRG_F_GRU needs the cluster kernels (H in {128, 256}, T > 1)");
   char* ws = (char*)workspace;
   float* bias_pack = (float*)ws;
   ws += align_up((size_t)D * 4 * H * sizeof(float), 256);
@@ -168,6 +171,7 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   r.trace = debug_trace_buffer();
   r.cluster_budget = (flags >> 16) & 0xFF;
   r.bf16_gates = bf16 ? 1 : 0;
+  r.gru = gru ? 1 : 0;
   if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
   return rec_forward_generic(r, stream);
 }
@@ -211,6 +215,9 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   r.T = T; r.B = B; r.H = H; r.D = D;
   r.cluster_budget = (flags >> 16) & 0xFF;
   r.bf16_gates = bf16 ? 1 : 0;
+  r.gru = (flags & MRG_F_GRU) ? 1 : 0;
+  MRG_REQUIRE(!r.gru || (T > 1 && rec2_supported(H) && !(flags & MRG_F_GENERIC_REC)),
+              "mrg_lstm_layer_backward: MRG_F_GRU needs the cluster kernels (H in {128, 256}, T > 1)");
   int e = 0;
   // two-phase backward: MRG_F_BWD_NO_WGRAD = BPTT + bias sums + dX (what the previous layer waits for),
   // MRG_F_BWD_WGRAD_ONLY = the two weight-gradient GEMMs from the d(pre-activations) an earlier NO_WGRAD call left in

@@ -284,6 +284,7 @@ struct RecArgs {
   unsigned long long* trace;  // developer event trace (-DMRG_REC_TRACE builds), else nullptr
   int cluster_budget;         // > 0: use at most this many clusters (MRG_F_CLUSTER_BUDGET)
   int bf16_gates;             // bf16 mode: `gates` holds 4 x bfloat16 per hidden unit (8 bytes) instead of 4 x fp32
+  int gru;                    // MRG_F_GRU: the four gate rows are (r, z, 0, n) of a GRU, the tail applies the GRU cell
 };
 unsigned long long* debug_trace_buffer();
 int rec_forward_generic(const RecArgs& a, cudaStream_t stream);
@@ -302,6 +303,7 @@ struct RecBwdArgs {
   int T, B, H, D;
   int cluster_budget;   // same meaning as in RecArgs
   int bf16_gates;       // same meaning as in RecArgs: gates in, d(pre-activations) out, both bfloat16
+  int gru;              // same meaning as in RecArgs
 };
 int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 // cluster kernels (chunk-pipelined, H in {128, 256})

@@ -101,7 +101,13 @@ __device__ __forceinline__ void cpb_wait_dyn(int n) {  // n uniform: at most n g
 
 constexpr int BWD2_THREADS = 512;  // warps 0-7: body (FFMA2) role, warps 8-15: head role
 
-template <int H, int RBC>
+// GRU = true (see rec_fwd2_kernel): reserve in = (r, z, n, q) with q = W_hn h + b_hn; with dh the gradient at h_t,
+//     d(n) = dh (1 - z), d(z) = dh (h_{t-1} - n); dn_pre = d(n) (1 - n^2), dr_pre = dn_pre q r (1 - r), dz_pre = d(z) z (1 - z)
+// reserve out = (dr_pre, dz_pre, dn_pre, dn_pre r): slots (0, 1, 2) are the gradient at the x-projection, slots (0, 1, 3) at
+// the recurrent projection — with W_ih rows (r, z, n, 0) and W_hh rows (r, z, 0, n) ONE four-slot vector serves dX, both
+// weight gradients, both bias gradients and the transposed mat-vec of the body warps.  The direct path dh z to h_{t-1}
+// is carried in the slot the LSTM uses for d(c).
+template <int H, int RBC, bool GRU>
 __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a, int slices, int nch) {
   using Cfg = Bwd2Cfg<H>;
   using Chunk = Bwd2Chunk<H, RBC>;
@@ -124,7 +130,8 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
   // reserve of this direction: (i, f, g, o) in, d(pre-activations) out; 16 bytes per unit in fp32, 8 in the bf16 mode
   const bool bf = a.bf16_gates != 0;
   char* gates_b = reinterpret_cast<char*>(a.gates) + (size_t)d * T * B * 4 * H * (bf ? 2 : 4);
-  const float* c_ext = a.c_ext + (size_t)d * (T + 1) * B * H;
+  // state saved by the forward that the head reads one step back: c_{t-1} (LSTM) or h_{t-1} (GRU)
+  const float* c_ext = (GRU ? a.y_ext : a.c_ext) + (size_t)d * (T + 1) * B * H;
 
   // ---- shared-memory state (all 12 warps) -------------------------------------------------------------------
   for (int ch = 0; ch < nch; ++ch) {
@@ -178,11 +185,11 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
           const size_t row = crow0 + r;
           C.db[r][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
           C.dy[r][lane] = 0.f;
-          C.dc[r][lane] = a.dc_n ? a.dc_n[((size_t)d * B + row) * H + j] : 0.f;
+          C.dc[r][lane] = (!GRU && a.dc_n) ? a.dc_n[((size_t)d * B + row) * H + j] : 0.f;
           if (T > 0) {
             const int t_last = d == 0 ? T - 1 : 0;
             const int out_slot = d == 0 ? t_last + 1 : t_last;
-            C.c_cur[r][lane] = c_ext[((size_t)out_slot * B + row) * H + j];
+            C.c_cur[r][lane] = GRU ? 0.f : c_ext[((size_t)out_slot * B + row) * H + j];
             prefetch(C, crow0, T - 1);
           }
           // the first iteration reads dh_n through source slot 0 of part[0]
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
           const float4 g = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.g[r][lane])) : C.g[r][lane];
           const float cprev = C.cp[r][lane];
           float dh = C.dy[r][lane];
-          const float tc = fast_tanh(C.c_cur[r][lane]);
+          const float tc = GRU ? 0.f : fast_tanh(C.c_cur[r][lane]);
           const float dcin = C.dc[r][lane];
           if (iter + 1 < T) prefetch(C, crow0, step - 1);
           const uint32_t hbar_cur = smem_u32(&C.hbar[cur]);
@@ -223,16 +230,27 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
           if (iter > 0) mbar_wait(smem_u32(&C.rbar), (uint32_t)((iter - 1) & 1));
 #pragma unroll
           for (int s = 0; s < CL; ++s) dh += C.part[cur][s][r][lane];
-          const float d_o = dh * tc;
-          const float dct = dcin + dh * g.w * (1.f - tc * tc);
-          const float d_i = dct * g.z, d_g = dct * g.x, d_f = dct * cprev;
-          const float4 dp = make_float4(d_i * g.x * (1.f - g.x), d_f * g.y * (1.f - g.y), d_g * (1.f - g.z * g.z),
-                                        d_o * g.w * (1.f - g.w));
+          float4 dp;
+          float carry;
+          if (GRU) {
+            dh += dcin;                                            // direct path dh_{t+1} z_{t+1}
+            const float dnp = dh * (1.f - g.y) * (1.f - g.z * g.z);
+            const float dzp = dh * (cprev - g.z) * g.y * (1.f - g.y);   // cprev = h_{t-1}
+            dp = make_float4(dnp * g.w * g.x * (1.f - g.x), dzp, dnp, dnp * g.x);
+            carry = dh * g.y;
+          } else {
+            const float d_o = dh * tc;
+            const float dct = dcin + dh * g.w * (1.f - tc * tc);
+            const float d_i = dct * g.z, d_g = dct * g.x, d_f = dct * cprev;
+            dp = make_float4(d_i * g.x * (1.f - g.x), d_f * g.y * (1.f - g.y), d_g * (1.f - g.z * g.z),
+                             d_o * g.w * (1.f - g.w));
+            carry = dct * g.y;
+          }
           *reinterpret_cast<float4*>(&C.dpre[r][lane * 4]) = dp;
           __syncwarp();
           if (lane == 0) mbarb_arrive_local(smem_u32(&C.dbar));
-          C.dc[r][lane] = dct * g.y;
-          C.c_cur[r][lane] = cprev;
+          C.dc[r][lane] = carry;
+          if (!GRU) C.c_cur[r][lane] = cprev;
           float4 db = C.db[r][lane];
           db.x += dp.x; db.y += dp.y; db.z += dp.z; db.w += dp.w;
           C.db[r][lane] = db;
@@ -260,8 +278,8 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
       for (int s = 0; s < CL; ++s) dh += C.part[fin][s][r][lane];
       float* dh0 = d == 0 ? a.dh0[0] : a.dh0[1];
       float* dc0 = d == 0 ? a.dc0[0] : a.dc0[1];
-      if (dh0) dh0[row * H + j] = dh;
-      if (dc0) dc0[row * H + j] = C.dc[r][lane];
+      if (dh0) dh0[row * H + j] = GRU ? dh + C.dc[r][lane] : dh;
+      if (dc0 && !GRU) dc0[row * H + j] = C.dc[r][lane];
       *reinterpret_cast<float4*>(a.db_part + (((size_t)d * B + row) * H + j) * 4) = C.db[r][lane];
     }
     return;
@@ -363,11 +381,11 @@ __global__ void __launch_bounds__(BWD2_THREADS, 1) rec_bwd2_kernel(RecBwdArgs a,
   }
 }
 
-template <int H, int RBC>
+template <int H, int RBC, bool GRU>
 static int launch_bwd2(const RecBwdArgs& a, int slices, int nch, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    MRG_CUDA_CHECK(cudaFuncSetAttribute(rec_bwd2_kernel<H, RBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(rec_bwd2_kernel<H, RBC, GRU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(rec2_max_chunks(H, RBC) * sizeof(Bwd2Chunk<H, RBC>))));
     attr_set = true;
   }
@@ -384,10 +402,10 @@ static int launch_bwd2(const RecBwdArgs& a, int slices, int nch, cudaStream_t st
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static char name[64];
-  if (!name[0]) snprintf(name, sizeof(name), "mrg::rec_bwd2_kernel<%d, %d>", H, RBC);
+  if (!name[0]) snprintf(name, sizeof(name), GRU ? "mrg::rec_bwd2_kernel<%d, %d, gru>" : "mrg::rec_bwd2_kernel<%d, %d>", H, RBC);
   ProfScope prof(PROF_REC_BWD, stream, name);
   count_launch();
-  MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_bwd2_kernel<H, RBC>, a, slices, nch));
+  MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_bwd2_kernel<H, RBC, GRU>, a, slices, nch));
   return 0;
 }
 
@@ -396,8 +414,12 @@ int rec_backward_cluster2(const RecBwdArgs& a, cudaStream_t stream) {
               "rec_backward_cluster2: T*B*4H*D exceeds the 32-bit index range");
   int slices, nch, rbc;
   pick_partition2(a.H, a.B, a.D, a.cluster_budget, &slices, &nch, &rbc);
-  if (a.H == 256) return rbc == 2 ? launch_bwd2<256, 2>(a, slices, nch, stream) : launch_bwd2<256, 4>(a, slices, nch, stream);
-  if (a.H == 128) return rbc == 2 ? launch_bwd2<128, 2>(a, slices, nch, stream) : launch_bwd2<128, 4>(a, slices, nch, stream);
+  if (a.gru) {
+    if (a.H == 256) return rbc == 2 ? launch_bwd2<256, 2, true>(a, slices, nch, stream) : launch_bwd2<256, 4, true>(a, slices, nch, stream);
+    if (a.H == 128) return rbc == 2 ? launch_bwd2<128, 2, true>(a, slices, nch, stream) : launch_bwd2<128, 4, true>(a, slices, nch, stream);
+  }
+  if (a.H == 256) return rbc == 2 ? launch_bwd2<256, 2, false>(a, slices, nch, stream) : launch_bwd2<256, 4, false>(a, slices, nch, stream);
+  if (a.H == 128) return rbc == 2 ? launch_bwd2<128, 2, false>(a, slices, nch, stream) : launch_bwd2<128, 4, false>(a, slices, nch, stream);
   set_error("rec_backward_cluster2: unsupported hidden size %d", a.H);
   return MRG_E_UNSUPPORTED;
 }

@@ -105,7 +105,13 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {  // n uniform: at mos
 
 constexpr int FWD2_THREADS = 512;  // warps 0-7: FFMA2 role, warps 8-15: tail role
 
-template <int H, int RBC>
+// GRU = true: the same recurrence machinery runs a GRU (lstmformer's GRU mixer, nn.GRU at mixer_block.py:194).  The caller
+// hands the weights in four-gate form — W_ih rows (r, z, n, 0), W_hh rows (r, z, 0, n), bias (b_ir + b_hr, b_iz + b_hz,
+// b_in, b_hn) — so that per hidden unit the x-projection slot holds (x_r, x_z, x_n, b_hn) and the recurrent sums are
+// (h_r, h_z, 0, h_n); only the cell in the tail differs:
+//     r = sig(x_r + h_r), z = sig(x_z + h_z), n = tanh(x_n + r (h_n + b_hn)), h' = n + z (h - n)       (torch.nn.GRU)
+// reserve = (r, z, n, h_n + b_hn); there is no cell state.
+template <int H, int RBC, bool GRU>
 __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, int slices, int nch) {
   using Cfg = Fwd2Cfg<H>;
   using Chunk = Fwd2Chunk<H, RBC>;
@@ -225,12 +231,23 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, in
           for (int i = 0; i < 2; ++i) {
             p[i].x += p[i + 2].x; p[i].y += p[i + 2].y; p[i].z += p[i + 2].z; p[i].w += p[i + 2].w;
           }
-          const float gi = fast_sigmoid((p[0].x + p[1].x) + xg.x);
-          const float gf = fast_sigmoid((p[0].y + p[1].y) + xg.y);
-          const float gg = fast_tanh((p[0].z + p[1].z) + xg.z);
-          const float go = fast_sigmoid((p[0].w + p[1].w) + xg.w);
-          const float cn = fmaf(gf, cold, gi * gg);
-          const float h = go * fast_tanh(cn);
+          float gi, gf, gg, go, cn, h;
+          if (GRU) {
+            gi = fast_sigmoid((p[0].x + p[1].x) + xg.x);                 // r
+            gf = fast_sigmoid((p[0].y + p[1].y) + xg.y);                 // z
+            go = (p[0].w + p[1].w) + xg.w;                               // W_hn h + b_hn
+            gg = fast_tanh(fmaf(gi, go, xg.z));                          // n
+            const float hprev = C.h[cur][r][j0 + lane];
+            cn = 0.f;
+            h = fmaf(gf, hprev - gg, gg);
+          } else {
+            gi = fast_sigmoid((p[0].x + p[1].x) + xg.x);
+            gf = fast_sigmoid((p[0].y + p[1].y) + xg.y);
+            gg = fast_tanh((p[0].z + p[1].z) + xg.z);
+            go = fast_sigmoid((p[0].w + p[1].w) + xg.w);
+            cn = fmaf(gf, cold, gi * gg);
+            h = go * fast_tanh(cn);
+          }
           if (send) {
             float4 hv;  // h of units 4q .. 4q+3, q = lane / 4
             hv.x = __shfl_sync(0xffffffffu, h, (lane & ~3));
@@ -245,9 +262,11 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) rec_fwd2_kernel(RecArgs a, in
               if ((lane & 3) + 4 * i < CL) st_async_v4(remote_base[i] + off_h, hv, remote_base[i] + off_bar);
           }
           REC_TRACE(12, ch, step);
-          C.c[r][lane] = cn;
           y_ext[obase + rj] = h;
-          c_ext[obase + rj] = cn;
+          if (!GRU) {
+            C.c[r][lane] = cn;
+            c_ext[obase + rj] = cn;
+          }
           if (a.train) {
             const size_t gidx = (size_t)((uint32_t)t * BH + rj);
             if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(gi, gf, gg, go);
@@ -313,12 +332,12 @@ int rec2_max_chunks(int H, int rbc) {
   return rbc == 2 ? 12 : 8;
 }
 
-template <int H, int RBC>
+template <int H, int RBC, bool GRU>
 static int launch_fwd2(const RecArgs& a, int slices, int nch, cudaStream_t stream) {
   static bool attr_set = false;
   const size_t smem = (size_t)nch * sizeof(Fwd2Chunk<H, RBC>);
   if (!attr_set) {
-    MRG_CUDA_CHECK(cudaFuncSetAttribute(rec_fwd2_kernel<H, RBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(rec_fwd2_kernel<H, RBC, GRU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(rec2_max_chunks(H, RBC) * sizeof(Fwd2Chunk<H, RBC>))));
     attr_set = true;
   }
@@ -335,16 +354,16 @@ static int launch_fwd2(const RecArgs& a, int slices, int nch, cudaStream_t strea
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static char name[64];
-  if (!name[0]) snprintf(name, sizeof(name), "mrg::rec_fwd2_kernel<%d, %d>", H, RBC);
+  if (!name[0]) snprintf(name, sizeof(name), GRU ? "mrg::rec_fwd2_kernel<%d, %d, gru>" : "mrg::rec_fwd2_kernel<%d, %d>", H, RBC);
   ProfScope prof(PROF_REC_FWD, stream, name);
   count_launch();
-  MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_fwd2_kernel<H, RBC>, a, slices, nch));
+  MRG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rec_fwd2_kernel<H, RBC, GRU>, a, slices, nch));
   return 0;
 }
 
 template <int H>
 static int max_clusters_fwd2() {
-  if (cudaFuncSetAttribute(rec_fwd2_kernel<H, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(rec_fwd2_kernel<H, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(12 * sizeof(Fwd2Chunk<H, 2>))) != cudaSuccess) {
     cudaGetLastError();
     return 0;
@@ -361,7 +380,7 @@ static int max_clusters_fwd2() {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, rec_fwd2_kernel<H, 2>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, rec_fwd2_kernel<H, 2, false>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -421,8 +440,12 @@ int rec_forward_cluster2(const RecArgs& a, cudaStream_t stream) {
               "rec_forward_cluster2: T*B*4H exceeds the 32-bit index range of one direction");
   int slices, nch, rbc;
   pick_partition2(a.H, a.B, a.D, a.cluster_budget, &slices, &nch, &rbc);
-  if (a.H == 256) return rbc == 2 ? launch_fwd2<256, 2>(a, slices, nch, stream) : launch_fwd2<256, 4>(a, slices, nch, stream);
-  if (a.H == 128) return rbc == 2 ? launch_fwd2<128, 2>(a, slices, nch, stream) : launch_fwd2<128, 4>(a, slices, nch, stream);
+  if (a.gru) {
+    if (a.H == 256) return rbc == 2 ? launch_fwd2<256, 2, true>(a, slices, nch, stream) : launch_fwd2<256, 4, true>(a, slices, nch, stream);
+    if (a.H == 128) return rbc == 2 ? launch_fwd2<128, 2, true>(a, slices, nch, stream) : launch_fwd2<128, 4, true>(a, slices, nch, stream);
+  }
+  if (a.H == 256) return rbc == 2 ? launch_fwd2<256, 2, false>(a, slices, nch, stream) : launch_fwd2<256, 4, false>(a, slices, nch, stream);
+  if (a.H == 128) return rbc == 2 ? launch_fwd2<128, 2, false>(a, slices, nch, stream) : launch_fwd2<128, 4, false>(a, slices, nch, stream);
   set_error("rec_forward_cluster2: unsupported hidden size %d", a.H);
   return MRG_E_UNSUPPORTED;
 }

@@ -4,8 +4,15 @@ mixer_block.py:194,207 ``GRUMixer.mixer``, selected by ``emb_mixers: gru`` in mr
 Same constructor, parameter names / shapes / init order and ``state_dict`` as ``nn.GRU`` (``weight_ih_l0`` [3H, I],
 gate order r, z, n); ``forward`` is replaced: the time-parallel ``x W_ih^T + b_ih`` and the four backward
 contractions (dX, dW_ih, dW_hh and the two bias column sums) run on the library's tcgen05 3xTF32 GEMM / column-sum
-kernels, the recurrence on ``mrg_gru_forward`` / ``mrg_gru_backward`` (csrc/mrg_gru.cu).  No cuDNN, no CPU path.
-Layers and directions are composed here (a reverse direction runs the same kernels on the time-flipped sequence)."""
+kernels.  The recurrence runs
+* for H in {128, 256} and T > 1 on the CLUSTER-RESIDENT recurrent kernels of the LSTM path (``rec_fwd2 / rec_bwd2_kernel<..,
+  gru>``, flag ``MRG_F_GRU``): the GRU's three gates are laid out in the LSTM's four gate slots — W_ih rows (r, z, n, 0),
+  W_hh rows (r, z, 0, n), bias (b_ir + b_hr, b_iz + b_hz, b_in, b_hn) — built here with differentiable torch ops, so one
+  four-slot d(pre-activation) vector serves dX, both weight gradients and both bias gradients and autograd routes every
+  block to the right ``nn.GRU`` parameter (the zero blocks receive the unused products);
+* otherwise on the generic ``mrg_gru_forward`` / ``mrg_gru_backward`` (csrc/mrg_gru.cu: any hidden size, W_hh streamed
+  from L2), composed per layer and direction below (a reverse direction runs on the time-flipped sequence).
+No cuDNN, no CPU path."""
 from __future__ import annotations
 
 from typing import Optional
@@ -16,7 +23,17 @@ from torch.nn import functional as F
 
 from . import _cabi
 from .linear import _colsum, _gemm, fused_grad_target
-from .lstm import _default_flags
+from .lstm import _LSTMLayerFn, _default_flags
+
+
+def _four_gate_weights(w_ih, w_hh, b_ih, b_hh, H):
+    """nn.GRU parameters of one direction -> the four-gate form of MRG_F_GRU (include/mrg_lstm.h)."""
+    w_ih4 = torch.cat([w_ih, w_ih.new_zeros(H, w_ih.shape[1])], dim=0)                 # (r, z, n, 0)
+    w_hh4 = torch.cat([w_hh[:2 * H], w_hh.new_zeros(H, H), w_hh[2 * H:]], dim=0)       # (r, z, 0, n)
+    if b_ih is None:
+        return w_ih4, w_hh4, None, None
+    b4 = torch.cat([b_ih[:2 * H] + b_hh[:2 * H], b_ih[2 * H:], b_hh[2 * H:]])          # (b_r, b_z, b_in, b_hn)
+    return w_ih4, w_hh4, b4, None
 
 
 class _GRULayerFn(torch.autograd.Function):
@@ -109,7 +126,23 @@ class B200GRU(nn.GRU):
         if T == 0:
             raise RuntimeError("B200GRU: empty sequence")
         h_n = []
+        Hs = self.hidden_size
+        flags = _default_flags()
+        cluster = Hs in (128, 256) and T > 1 and not flags & _cabi.F_GENERIC_REC
         for layer in range(self.num_layers):
+            if cluster:   # both directions in one launch on the cluster-resident kernels
+                ws = []
+                for d in range(D):
+                    sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
+                    ws += _four_gate_weights(getattr(self, "weight_ih" + sfx), getattr(self, "weight_hh" + sfx),
+                                             getattr(self, "bias_ih" + sfx) if self.bias else None,
+                                             getattr(self, "bias_hh" + sfx) if self.bias else None, Hs)
+                h0 = None if hx is None else hx[layer * D:(layer + 1) * D]
+                x, hl, _ = _LSTMLayerFn.apply(x, h0, None, D, Hs, (flags & ~_cabi.F_BF16) | _cabi.F_GRU, *ws)
+                h_n += [hl[d] for d in range(D)]
+                if self.dropout > 0.0 and self.training and layer + 1 < self.num_layers:
+                    x = F.dropout(x, self.dropout, True)
+                continue
             outs = []
             for d in range(D):
                 sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")

@@ -449,7 +449,11 @@ def test_metaformer_headline_shape_trains_through_the_trainer():
 # GRU mixer (lstmformer with emb_mixers: gru): B200GRU against torch.nn.GRU fp64, the mixer stack against the reference
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("I,H,L,bi,B,T,with_hx", [
-    (256, 256, 1, False, 64, 20, False),   # lstmformer mixer shape
+    (256, 256, 1, False, 64, 20, False),   # lstmformer mixer shape -> cluster-resident kernels (MRG_F_GRU)
+    (256, 256, 2, False, 7, 23, True),     # cluster kernels: two layers, carried state, ragged row group
+    (128, 256, 1, True, 31, 9, True),      # cluster kernels: both directions in one launch
+    (128, 128, 2, False, 16, 33, True),    # cluster kernels, H = 128
+    (256, 256, 1, False, 64, 300, False),  # cluster kernels at the benchmark length
     (32, 32, 2, False, 3, 9, True),        # two layers, carried state, ragged row group
     (20, 16, 1, True, 5, 7, True),         # bidirectional
     (256, 256, 1, False, 1, 1, True),      # a single frame (autoregressive step)
