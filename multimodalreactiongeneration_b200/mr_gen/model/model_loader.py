@@ -16,5 +16,7 @@ def load_model(model_type: str, model_path: str, cfg):
     else:
         raise ValueError(f"invalid model type: {model_type}")
     model = cls(cfg.model, cfg.optim, cfg.metrics)
-    model.load_state_dict(torch.load(model_path, map_location="cpu")["state_dict"])
+    # the reference's checkpoints are Lightning .ckpt files (pickled non-tensor objects next to the state_dict): they are
+    # the user's own training output, loaded as the reference does (torch >= 2.6 defaults to weights_only=True)
+    model.load_state_dict(torch.load(model_path, map_location="cpu", weights_only=False)["state_dict"])
     return model

@@ -331,7 +331,7 @@ class Trainer:
                 rec["val_loss"] = self.validate(val_batches(epoch))
             history.append(rec)
             if self.ckpt_dir and _rank() == 0:
-                save_checkpoint(self.model, os.path.join(self.ckpt_dir, "last.ckpt"), epoch, self.global_step)
+                save_checkpoint(self.model, os.path.join(self.ckpt_dir, "last.ckpt"), epoch, self.global_step, trainer=self)
         return history
 
 
@@ -343,16 +343,40 @@ def _rank() -> int:
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
-def save_checkpoint(model: nn.Module, path: str, epoch: int = 0, global_step: int = 0) -> None:
-    """Lightning-shaped ``.ckpt``: a dict whose ``"state_dict"`` has the reference's keys."""
+def save_checkpoint(model: nn.Module, path: str, epoch: int = 0, global_step: int = 0, trainer=None) -> None:
+    """Lightning-shaped ``.ckpt``: a dict whose ``"state_dict"`` has the reference's keys.  With ``trainer`` the
+    optimizer / LR-scheduler state is stored as Lightning does (``optimizer_states``, ``lr_schedulers``); the moments of
+    the fused flat AdamW (which torch's ``optimizer.state_dict()`` does not see) go under ``flat_adamw``."""
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
-                "epoch": epoch, "global_step": global_step}, path)
+    ckpt = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+            "epoch": epoch, "global_step": global_step}
+    if trainer is not None:
+        ckpt["optimizer_states"] = [trainer.optimizer.state_dict()]
+        ckpt["lr_schedulers"] = [trainer.scheduler.state_dict()] if trainer.scheduler is not None else []
+        if trainer.flat_opt is not None:
+            fo = trainer.flat_opt
+            ckpt["flat_adamw"] = {"exp_avg": fo.exp_avg.detach().cpu(), "exp_avg_sq": fo.exp_avg_sq.detach().cpu(),
+                                  "state": fo.state.detach().cpu(),
+                                  "names": [n for n, _ in model.named_parameters() if _.requires_grad]}
+    torch.save(ckpt, path)
 
 
-def load_checkpoint(model: nn.Module, path: str, map_location="cpu") -> Dict:
-    ckpt = torch.load(path, map_location=map_location)
+def load_checkpoint(model: nn.Module, path: str, map_location="cpu", trainer=None, trusted: bool = True) -> Dict:
+    """``trusted=True`` (a checkpoint you wrote, or a Lightning ``.ckpt`` of the reference, which pickles non-tensor
+    objects) loads with ``weights_only=False``; pass ``trusted=False`` for files of unknown origin."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=not trusted)
     model.load_state_dict(ckpt["state_dict"])
+    if trainer is not None:
+        if ckpt.get("optimizer_states"):
+            trainer.optimizer.load_state_dict(ckpt["optimizer_states"][0])
+        if ckpt.get("lr_schedulers") and trainer.scheduler is not None:
+            trainer.scheduler.load_state_dict(ckpt["lr_schedulers"][0])
+        fa = ckpt.get("flat_adamw")
+        if fa is not None and trainer.flat_opt is not None and fa["exp_avg"].numel() == trainer.flat_opt.exp_avg.numel():
+            trainer.flat_opt.exp_avg.copy_(fa["exp_avg"])
+            trainer.flat_opt.exp_avg_sq.copy_(fa["exp_avg_sq"])
+            trainer.flat_opt.state.copy_(fa["state"])
+        trainer.global_step = int(ckpt.get("global_step", trainer.global_step))
     return ckpt
 
 

@@ -292,6 +292,36 @@ def test_trainer_uses_fused_optimizer_and_keeps_state_dict_keys():
     assert l1 < l0
 
 
+def test_checkpoint_resume_restores_fused_optimizer_state(tmp_path):
+    """save_checkpoint(trainer=...) / load_checkpoint(trainer=...): a resumed trainer (fresh model object, fresh fused
+    AdamW) continues the trajectory of the original one — parameters after the next step are identical."""
+    from multimodalreactiongeneration_b200.mr_gen.configs import simple_lstm_cfg
+    from multimodalreactiongeneration_b200.mr_gen.model.simple_lstm.simple_lstm import SimpleLSTM
+    from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer, load_checkpoint, save_checkpoint
+    g = torch.Generator().manual_seed(3)
+    batch = (torch.randn(4, 20, 80, generator=g).cuda(), torch.randn(4, 20, 6, generator=g).cuda(),
+             torch.randn(4, 1, 6, generator=g).cuda())
+    torch.manual_seed(0)
+    model = SimpleLSTM(*simple_lstm_cfg()).cuda()
+    tr = Trainer(model)
+    tr.optimizer.param_groups[0]["lr"] = 1e-3
+    for _ in range(3):
+        tr.train_step(batch)
+    path = str(tmp_path / "ckpts" / "simple_lstm" / "last.ckpt")
+    save_checkpoint(model, path, epoch=0, global_step=tr.global_step, trainer=tr)
+    tr.train_step(batch)
+    want = {k: v.clone() for k, v in model.state_dict().items()}
+    torch.manual_seed(123)   # a different initialisation: everything must come from the file
+    model2 = SimpleLSTM(*simple_lstm_cfg()).cuda()
+    tr2 = Trainer(model2)
+    ck = load_checkpoint(model2, path, trainer=tr2)
+    assert "optimizer_states" in ck and "flat_adamw" in ck
+    assert tr2.optimizer.param_groups[0]["lr"] == 1e-3
+    tr2.train_step(batch)
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, want[k]) or rel_err(v, want[k]) <= 1e-6, k
+
+
 @pytest.mark.parametrize("kdim,same_kv", [(None, True), (None, False), (96, True)])
 def test_b200_multihead_attention_matches_torch(kdim, same_kv):
     """Projections on the tcgen05 GEMM, SDPA from torch: forward / input / parameter gradients vs nn.MultiheadAttention
