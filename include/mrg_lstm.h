@@ -250,6 +250,10 @@ int mrg_adamw_flat(float* p, float* g, float* m, float* v, size_t n, const float
  * mask_mode 0: none | 1: key j visible to query i iff j / rate <= i | 2: iff j <= i / rate; additionally (i, j) is
  * masked when pad_q[b*Tq+i] and pad_k[b*Tk+j] are both non-zero (both NULL = no padding).  A query with no visible
  * key yields 0 (torch: NaN).  lse [B,nh,Tq] (log2 domain) is saved for the backward; dvec [B,nh,Tq] is scratch. */
+/* Which kernels the two calls below run (process-wide): 0 = warp-level tensor cores with the 3xTF32 split (default,
+ * fp32-grade: csrc/mrg_attention_mma.cu), 1 = one tf32 pass (the tf32 / bf16 precision modes), 2 = the CUDA-core fp32
+ * kernels (csrc/mrg_attention.cu, cross-check). */
+int mrg_attention_set_mode(int mode);
 int mrg_attention_forward(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
                           int ldo, float* lse, int B, int nh, int Tq, int Tk, int hd, float scale, int mask_mode,
                           int rate, const uint8_t* pad_q, const uint8_t* pad_k, void* stream);

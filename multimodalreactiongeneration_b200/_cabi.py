@@ -23,7 +23,7 @@ EXPORTS = (
     "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
     "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward", "mrg_profile_kernel_name",
     "mrg_lstm_pack_floats", "mrg_split_tf32", "mrg_gemm_split_supported", "mrg_gemm_strided_split",
-    "mrg_audio_features",
+    "mrg_audio_features", "mrg_attention_set_mode",
 )
 
 
@@ -132,6 +132,8 @@ def lib() -> ctypes.CDLL:
                                         c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p]
     L.mrg_attention_forward.restype = c_int
+    L.mrg_attention_set_mode.argtypes = [c_int]
+    L.mrg_attention_set_mode.restype = c_int
     L.mrg_attention_backward.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                          c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                          c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p,

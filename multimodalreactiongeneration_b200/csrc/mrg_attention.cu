@@ -467,12 +467,29 @@ static int attn_check(const char* who, const AttnArgs& a, int hd) {
   MRG_REQUIRE((a.pad_q == nullptr) == (a.pad_k == nullptr), "%s: pad_q and pad_k go together", who);
   return 0;
 }
+int attn_mma_launch(const AttnArgs& a, int hd, int backward, int passes, cudaStream_t stream);   // mrg_attention_mma.cu
+
+// 0: warp-level tensor cores, 3xTF32 (default, fp32-grade) | 1: one tf32 pass (reduced-precision modes) |
+// 2: the CUDA-core fp32 kernels of this file (cross-check; MRG_ATTENTION_SIMT=1 forces it)
+static int g_attn_mode = 0;
 static int attn_dispatch(const AttnArgs& a, int hd, int backward, cudaStream_t stream) {
+  static int force_simt = -1;
+  if (force_simt < 0) {
+    const char* e = getenv("MRG_ATTENTION_SIMT");
+    force_simt = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!force_simt && g_attn_mode != 2) return attn_mma_launch(a, hd, backward, g_attn_mode == 1 ? 1 : 3, stream);
   return hd == 32 ? attn_launch<32>(a, backward, stream) : attn_launch<64>(a, backward, stream);
 }
 #define AT_ALIGNED(p, ld) ((p) != nullptr && (((uintptr_t)(p)) & 15) == 0 && (ld) % 4 == 0 && (ld) >= nh * hd)
 
 }  // namespace mrg
+
+extern "C" int mrg_attention_set_mode(int mode) {
+  MRG_REQUIRE(mode >= 0 && mode <= 2, "mrg_attention_set_mode: 0 (3xTF32 tensor cores), 1 (one tf32 pass) or 2 (CUDA cores)");
+  mrg::g_attn_mode = mode;
+  return 0;
+}
 
 extern "C" int mrg_attention_forward(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
                                      int ldo, float* lse, int B, int nh, int Tq, int Tk, int hd, float scale,

@@ -84,6 +84,8 @@ def set_precision(mode: str) -> None:
     if mode not in ("fp32", "tf32", "bf16"):
         raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
     _PRECISION["mode"] = mode
+    if os.path.exists(_cabi.LIB_PATH):   # the attention kernels follow: 3xTF32 for fp32, one tf32 pass otherwise
+        _cabi.check(_cabi.lib().mrg_attention_set_mode(0 if mode == "fp32" else 1), "mrg_attention_set_mode")
 
 
 # Weight-gradient overlap: inside ``with wgrad_overlap():`` (the trainer wraps ``loss.backward()`` in it) a layer's backward
