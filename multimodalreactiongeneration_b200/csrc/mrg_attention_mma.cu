@@ -26,7 +26,18 @@
 namespace mrg {
 
 constexpr int AM_T = 64;          // rows of the resident tile / of a streamed tile
-constexpr int AM_THREADS = 128;   // 4 warps x 16 rows
+// A warp owns MT m-tiles of 16 rows (MT = 1: 4 warps per CTA, MT = 2: 2 warps): with MT = 2 every B fragment a warp loads
+// and splits feeds two MMAs per pass, which halves the load / split instructions per MMA — but at 230-255 registers per
+// thread only 8 warps stay resident per SM, and that costs more than the instructions save.  Measured (B200,
+// profiles/r2_attention.txt): MT = 1: 150 / 476 us forward / backward at the cfg 2 shape, 480 / 1757 us at the cfg 4 shape;
+// MT = 2: 172 / 489 and 888 / 1855.  MT = 1 is built; the template parameter stays for the next experiment.
+constexpr int am_threads(int MT) { return 32 * (4 / MT); }
+#ifndef AM_MT_FWD
+#define AM_MT_FWD 1
+#endif
+#ifndef AM_MT_BWD32
+#define AM_MT_BWD32 1
+#endif
 
 __device__ __forceinline__ void am_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -55,17 +66,21 @@ __device__ __forceinline__ void am_split_a(const float (&x)[4], uint32_t (&hi)[4
   }
 }
 
-// c[nt] += X[16 rows of this warp] . Y^T : c[nt][.] = sum_d X[row][d] Y[nt*8 + col][d]   (X, Y: [64][HD + 4] tiles)
-template <int HD, int PASSES>
-__device__ __forceinline__ void am_prod_nt(float (&c)[8][4], const float* X, const float* Y, int g, int q) {
+// c[mt][nt] += X[16 MT rows of this warp] . Y^T : c[mt][nt][.] = sum_d X[mt*16 + row][d] Y[nt*8 + col][d]
+// (X, Y: [64][HD + 4] tiles)
+template <int HD, int PASSES, int MT>
+__device__ __forceinline__ void am_prod_nt(float (&c)[MT][8][4], const float* X, const float* Y, int g, int q) {
   constexpr int LD = HD + 4;
 #pragma unroll
   for (int ks = 0; ks < HD / 8; ++ks) {
-    const float* xr = X + g * LD + ks * 8 + q;
-    const float xa[4] = {xr[0], xr[8 * LD], xr[4], xr[8 * LD + 4]};
-    uint32_t ahi[4], alo[4];
-    am_split_a<PASSES>(xa, ahi, alo);
-    // the three passes of one accumulator depend on each other: issue pass by pass ACROSS the 8 n-tiles so that
+    uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const float* xr = X + (mt * 16 + g) * LD + ks * 8 + q;
+      const float xa[4] = {xr[0], xr[8 * LD], xr[4], xr[8 * LD + 4]};
+      am_split_a<PASSES>(xa, ahi[mt], alo[mt]);
+    }
+    // the three passes of one accumulator depend on each other: issue pass by pass ACROSS the n-tiles so that
     // consecutive MMAs are independent
     float y0[8], y1[8];
     uint32_t h0[8], h1[8];
@@ -79,25 +94,38 @@ __device__ __forceinline__ void am_prod_nt(float (&c)[8][4], const float* X, con
     }
     if (PASSES == 3) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) am_mma(c[nt], alo, h0[nt], h1[nt]);
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) am_mma(c[nt], ahi, am_lo(y0[nt], h0[nt]), am_lo(y1[nt], h1[nt]));
+        for (int mt = 0; mt < MT; ++mt) am_mma(c[mt][nt], alo[mt], h0[nt], h1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t l0 = am_lo(y0[nt], h0[nt]), l1 = am_lo(y1[nt], h1[nt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) am_mma(c[mt][nt], ahi[mt], l0, l1);
+      }
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) am_mma(c[nt], ahi, h0[nt], h1[nt]);
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) am_mma(c[mt][nt], ahi[mt], h0[nt], h1[nt]);
   }
 }
 
-// o[dt] += P . Y : o[dt][.] = sum_j P[row][j] Y[j][dt*8 + col], P = the 16 x 64 block held as accumulator fragments
-template <int HD, int PASSES>
-__device__ __forceinline__ void am_prod_acc(float (&o)[HD / 8][4], const float (&p)[8][4], const float* Y, int g, int q) {
+// o[mt][dt] += P . Y : o[mt][dt][.] = sum_j P[mt][row][j] Y[j][dt*8 + col], P = the 16 MT x 64 block held as accumulator
+// fragments
+template <int HD, int PASSES, int MT>
+__device__ __forceinline__ void am_prod_acc(float (&o)[MT][HD / 8][4], const float (&p)[MT][8][4], const float* Y, int g,
+                                            int q) {
   constexpr int LD = HD + 4;
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
     // accumulator (row g: cols 2q, 2q+1 | row g+8: cols 2q, 2q+1) read as A with k = q <-> col 2q, k = q+4 <-> col 2q+1
-    const float pa[4] = {p[kk][0], p[kk][2], p[kk][1], p[kk][3]};
-    uint32_t ahi[4], alo[4];
-    am_split_a<PASSES>(pa, ahi, alo);
+    uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const float pa[4] = {p[mt][kk][0], p[mt][kk][2], p[mt][kk][1], p[mt][kk][3]};
+      am_split_a<PASSES>(pa, ahi[mt], alo[mt]);
+    }
     const float* yp = Y + (kk * 8 + 2 * q) * LD + g;
     float y0[HD / 8], y1[HD / 8];
     uint32_t h0[HD / 8], h1[HD / 8];
@@ -110,12 +138,20 @@ __device__ __forceinline__ void am_prod_acc(float (&o)[HD / 8][4], const float (
     }
     if (PASSES == 3) {
 #pragma unroll
-      for (int dt = 0; dt < HD / 8; ++dt) am_mma(o[dt], alo, h0[dt], h1[dt]);
+      for (int dt = 0; dt < HD / 8; ++dt)
 #pragma unroll
-      for (int dt = 0; dt < HD / 8; ++dt) am_mma(o[dt], ahi, am_lo(y0[dt], h0[dt]), am_lo(y1[dt], h1[dt]));
+        for (int mt = 0; mt < MT; ++mt) am_mma(o[mt][dt], alo[mt], h0[dt], h1[dt]);
+#pragma unroll
+      for (int dt = 0; dt < HD / 8; ++dt) {
+        const uint32_t l0 = am_lo(y0[dt], h0[dt]), l1 = am_lo(y1[dt], h1[dt]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) am_mma(o[mt][dt], ahi[mt], l0, l1);
+      }
     }
 #pragma unroll
-    for (int dt = 0; dt < HD / 8; ++dt) am_mma(o[dt], ahi, h0[dt], h1[dt]);
+    for (int dt = 0; dt < HD / 8; ++dt)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) am_mma(o[mt][dt], ahi[mt], h0[dt], h1[dt]);
   }
 }
 
@@ -130,7 +166,7 @@ __device__ __forceinline__ void am_wait1() { asm volatile("cp.async.wait_group 1
 template <int HD>
 __device__ __forceinline__ void am_load_tile(float* dst, const float* __restrict__ src, int ld, int r0, int nrows) {
   constexpr int C4 = HD / 4, LD = HD + 4;
-  for (int f = threadIdx.x; f < AM_T * C4; f += AM_THREADS) {
+  for (int f = threadIdx.x; f < AM_T * C4; f += blockDim.x) {
     const int r = f / C4, c = f % C4;
     float* d = dst + r * LD + c * 4;
     if (r0 + r < nrows) am_cp16(d, src + (size_t)(r0 + r) * ld + c * 4);
@@ -202,8 +238,8 @@ __device__ __forceinline__ void am_finish_scores(float (&s)[8][4], const AttnArg
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-template <int HD, int PASSES>
-__global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 4 : 2) attn_mma_fwd_kernel(AttnArgs a) {
+template <int HD, int PASSES, int MT>
+__global__ void __launch_bounds__(am_threads(MT), HD == 32 ? 4 : 2) attn_mma_fwd_kernel(AttnArgs a) {
   constexpr int LD = HD + 4, TILE = AM_T * LD, ND = HD / 8;
   extern __shared__ __align__(16) float am_sm[];
   float* Qs = am_sm;              // [64][LD]
@@ -221,11 +257,21 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 4 : 2) attn_mma_fwd_ker
   am_load_tile<HD>(KV + TILE, vb, a.ldv, 0, a.Tk);
   am_commit();
 
-  const int r0 = i0 + warp * 16 + g, r1 = r0 + 8;
-  const int lim0 = am_row_limit<true>(a, r0), lim1 = am_row_limit<true>(a, r1);
-  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, o[ND][4];
+  const int wrow = warp * 16 * MT;   // first row of this warp inside the tile
+  int row[MT][2], lim[MT][2];
+  float m[MT][2], l[MT][2], o[MT][ND][4];
 #pragma unroll
-  for (int dt = 0; dt < ND; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      row[mt][rr] = i0 + wrow + mt * 16 + g + 8 * rr;
+      lim[mt][rr] = am_row_limit<true>(a, row[mt][rr]);
+      m[mt][rr] = -INFINITY;
+      l[mt][rr] = 0.f;
+    }
+#pragma unroll
+    for (int dt = 0; dt < ND; ++dt) o[mt][dt][0] = o[mt][dt][1] = o[mt][dt][2] = o[mt][dt][3] = 0.f;
+  }
 
   for (int jt = 0; jt < njt; ++jt) {
     float* Ks = KV + (jt & 1) * 2 * TILE;
@@ -240,62 +286,69 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 4 : 2) attn_mma_fwd_ker
       am_wait0();
     }
     __syncthreads();
-    float s[8][4];
+    float s[MT][8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    am_prod_nt<HD, PASSES>(s, Qs + warp * 16 * LD, Ks, g, q);
-    am_finish_scores<true>(s, a, b, r0, r1, lim0, lim1, jt * AM_T, q);
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      float mx = -INFINITY;
+      for (int nt = 0; nt < 8; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+    am_prod_nt<HD, PASSES, MT>(s, Qs + wrow * LD, Ks, g, q);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][rr * 2], s[nt][rr * 2 + 1]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float mn = fmaxf(m[rr], mx);
-      const float alpha = mn == -INFINITY ? 1.f : ex2_ftz(m[rr] - mn);
-      float rs = 0.f;
+    for (int mt = 0; mt < MT; ++mt) {
+      am_finish_scores<true>(s[mt], a, b, row[mt][0], row[mt][1], lim[mt][0], lim[mt][1], jt * AM_T, q);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int rr = 0; rr < 2; ++rr) {
+        float mx = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float p = mn == -INFINITY ? 0.f : ex2_ftz(s[nt][rr * 2 + e] - mn);
-          s[nt][rr * 2 + e] = p;
-          rs += p;
+        for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[mt][nt][rr * 2], s[mt][nt][rr * 2 + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float mn = fmaxf(m[mt][rr], mx);
+        const float alpha = mn == -INFINITY ? 1.f : ex2_ftz(m[mt][rr] - mn);
+        float rs = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float p = mn == -INFINITY ? 0.f : ex2_ftz(s[mt][nt][rr * 2 + e] - mn);
+            s[mt][nt][rr * 2 + e] = p;
+            rs += p;
+          }
+        l[mt][rr] = l[mt][rr] * alpha + rs;   // this thread's share of the row sum (the quad is reduced at the end)
+        m[mt][rr] = mn;
+#pragma unroll
+        for (int dt = 0; dt < ND; ++dt) {
+          o[mt][dt][rr * 2] *= alpha;
+          o[mt][dt][rr * 2 + 1] *= alpha;
         }
-      l[rr] = l[rr] * alpha + rs;   // this thread's share of the row sum (the quad is reduced at the end)
-      m[rr] = mn;
-#pragma unroll
-      for (int dt = 0; dt < ND; ++dt) {
-        o[dt][rr * 2] *= alpha;
-        o[dt][rr * 2 + 1] *= alpha;
       }
     }
-    am_prod_acc<HD, PASSES>(o, s, Vs, g, q);
+    am_prod_acc<HD, PASSES, MT>(o, s, Vs, g, q);
     __syncthreads();
   }
   float* ob = a.o + (size_t)b * a.Tq * a.ldo + h * HD;
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    float lt = l[rr];
-    lt += __shfl_xor_sync(0xffffffffu, lt, 1);
-    lt += __shfl_xor_sync(0xffffffffu, lt, 2);
-    const int qi = rr ? r1 : r0;
-    if (qi >= a.Tq) continue;
-    const float inv = lt > 0.f ? 1.f / lt : 0.f;   // a query with no visible key gives 0 (torch: NaN)
-    float* orow = ob + (size_t)qi * a.ldo + 2 * q;
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int dt = 0; dt < ND; ++dt)
-      *reinterpret_cast<float2*>(orow + dt * 8) = make_float2(o[dt][rr * 2] * inv, o[dt][rr * 2 + 1] * inv);
-    if (q == 0 && a.lse) a.lse[(size_t)blockIdx.y * a.Tq + qi] = lt > 0.f ? m[rr] + log2f(lt) : 0.f;
-  }
+    for (int rr = 0; rr < 2; ++rr) {
+      float lt = l[mt][rr];
+      lt += __shfl_xor_sync(0xffffffffu, lt, 1);
+      lt += __shfl_xor_sync(0xffffffffu, lt, 2);
+      const int qi = row[mt][rr];
+      if (qi >= a.Tq) continue;
+      const float inv = lt > 0.f ? 1.f / lt : 0.f;   // a query with no visible key gives 0 (torch: NaN)
+      float* orow = ob + (size_t)qi * a.ldo + 2 * q;
+#pragma unroll
+      for (int dt = 0; dt < ND; ++dt)
+        *reinterpret_cast<float2*>(orow + dt * 8) = make_float2(o[mt][dt][rr * 2] * inv, o[mt][dt][rr * 2 + 1] * inv);
+      if (q == 0 && a.lse) a.lse[(size_t)blockIdx.y * a.Tq + qi] = lt > 0.f ? m[mt][rr] + log2f(lt) : 0.f;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // backward 1: dQ (and D = dO . O), query tile resident
 // ---------------------------------------------------------------------------------------------------------
-template <int HD, int PASSES>
-__global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dq_kernel(AttnArgs a) {
+template <int HD, int PASSES, int MT>
+__global__ void __launch_bounds__(am_threads(MT), HD == 32 ? 3 : 2) attn_mma_dq_kernel(AttnArgs a) {
   constexpr int LD = HD + 4, TILE = AM_T * LD, ND = HD / 8;
   extern __shared__ __align__(16) float am_sm[];
   float* Qs = am_sm;              // [64][LD]
@@ -317,30 +370,35 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dq_kern
   am_load_tile<HD>(KV + TILE, vb, a.ldv, 0, a.Tk);
   am_commit();
 
-  const int r0 = i0 + warp * 16 + g, r1 = r0 + 8;
-  const int lim0 = am_row_limit<true>(a, r0), lim1 = am_row_limit<true>(a, r1);
-  float lse[2] = {0.f, 0.f}, dvec[2];
+  const int wrow = warp * 16 * MT;
+  int row[MT][2], lim[MT][2];
+  float lse[MT][2], dvec[MT][2], acc[MT][ND][4];
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {   // D_i = dO_i . O_i: this thread's 2 * HD/8... columns, then the quad
-    const int qi = rr ? r1 : r0;
-    float d = 0.f;
-    if (qi < a.Tq) {
+  for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-      for (int dt = 0; dt < ND; ++dt) {
-        const float2 x = __ldg(reinterpret_cast<const float2*>(dob + (size_t)qi * a.lddo + dt * 8 + 2 * q));
-        const float2 y = __ldg(reinterpret_cast<const float2*>(ob + (size_t)qi * a.ldo + dt * 8 + 2 * q));
-        d = fmaf(x.x, y.x, fmaf(x.y, y.y, d));
+    for (int rr = 0; rr < 2; ++rr) {   // D_i = dO_i . O_i: this thread's columns, then the quad
+      const int qi = i0 + wrow + mt * 16 + g + 8 * rr;
+      row[mt][rr] = qi;
+      lim[mt][rr] = am_row_limit<true>(a, qi);
+      float d = 0.f;
+      lse[mt][rr] = 0.f;
+      if (qi < a.Tq) {
+#pragma unroll
+        for (int dt = 0; dt < ND; ++dt) {
+          const float2 x = __ldg(reinterpret_cast<const float2*>(dob + (size_t)qi * a.lddo + dt * 8 + 2 * q));
+          const float2 y = __ldg(reinterpret_cast<const float2*>(ob + (size_t)qi * a.ldo + dt * 8 + 2 * q));
+          d = fmaf(x.x, y.x, fmaf(x.y, y.y, d));
+        }
+        lse[mt][rr] = a.lse[(size_t)blockIdx.y * a.Tq + qi];
       }
-      lse[rr] = a.lse[(size_t)blockIdx.y * a.Tq + qi];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      dvec[mt][rr] = d;
+      if (q == 0 && qi < a.Tq) a.dvec[(size_t)blockIdx.y * a.Tq + qi] = d;
     }
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    dvec[rr] = d;
-    if (q == 0 && qi < a.Tq) a.dvec[(size_t)blockIdx.y * a.Tq + qi] = d;
-  }
-  float acc[ND][4];
 #pragma unroll
-  for (int dt = 0; dt < ND; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
+    for (int dt = 0; dt < ND; ++dt) acc[mt][dt][0] = acc[mt][dt][1] = acc[mt][dt][2] = acc[mt][dt][3] = 0.f;
+  }
 
   for (int jt = 0; jt < njt; ++jt) {
     float* Ks = KV + (jt & 1) * 2 * TILE;
@@ -355,43 +413,51 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dq_kern
       am_wait0();
     }
     __syncthreads();
-    float s[8][4], dp[8][4];
+    float s[MT][8][4], dp[MT][8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-    }
-    am_prod_nt<HD, PASSES>(s, Qs + warp * 16 * LD, Ks, g, q);
-    am_finish_scores<true>(s, a, b, r0, r1, lim0, lim1, jt * AM_T, q);
-    am_prod_nt<HD, PASSES>(dp, dOs + warp * 16 * LD, Vs, g, q);
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int rr = c >> 1;
-        const float p = ex2_ftz(s[nt][c] - lse[rr]);   // masked: ex2(-inf) = 0
-        s[nt][c] = p * (dp[nt][c] - dvec[rr]) * a.scale;
+      for (int nt = 0; nt < 8; ++nt) {
+        s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+        dp[mt][nt][0] = dp[mt][nt][1] = dp[mt][nt][2] = dp[mt][nt][3] = 0.f;
       }
-    am_prod_acc<HD, PASSES>(acc, s, Ks, g, q);
+    am_prod_nt<HD, PASSES, MT>(s, Qs + wrow * LD, Ks, g, q);
+    am_prod_nt<HD, PASSES, MT>(dp, dOs + wrow * LD, Vs, g, q);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      am_finish_scores<true>(s[mt], a, b, row[mt][0], row[mt][1], lim[mt][0], lim[mt][1], jt * AM_T, q);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int rr = c >> 1;
+          const float p = ex2_ftz(s[mt][nt][c] - lse[mt][rr]);   // masked: ex2(-inf) = 0
+          s[mt][nt][c] = p * (dp[mt][nt][c] - dvec[mt][rr]) * a.scale;
+        }
+    }
+    am_prod_acc<HD, PASSES, MT>(acc, s, Ks, g, q);
     __syncthreads();
   }
   float* dqb = a.dq + (size_t)b * a.Tq * a.lddq + h * HD;
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int qi = rr ? r1 : r0;
-    if (qi >= a.Tq) continue;
-    float* row = dqb + (size_t)qi * a.lddq + 2 * q;
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int dt = 0; dt < ND; ++dt) *reinterpret_cast<float2*>(row + dt * 8) = make_float2(acc[dt][rr * 2], acc[dt][rr * 2 + 1]);
-  }
+    for (int rr = 0; rr < 2; ++rr) {
+      const int qi = row[mt][rr];
+      if (qi >= a.Tq) continue;
+      float* rowp = dqb + (size_t)qi * a.lddq + 2 * q;
+#pragma unroll
+      for (int dt = 0; dt < ND; ++dt)
+        *reinterpret_cast<float2*>(rowp + dt * 8) = make_float2(acc[mt][dt][rr * 2], acc[mt][dt][rr * 2 + 1]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // backward 2: dK, dV, key tile resident; the score block is computed TRANSPOSED (rows = keys) so that P^T and dS^T are
 // the A operands of dV += P^T dO and dK += dS^T Q straight from the accumulator fragments
 // ---------------------------------------------------------------------------------------------------------
-template <int HD, int PASSES>
-__global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dkv_kernel(AttnArgs a) {
+template <int HD, int PASSES, int MT>
+__global__ void __launch_bounds__(am_threads(MT), HD == 32 ? 3 : 2) attn_mma_dkv_kernel(AttnArgs a) {
   constexpr int LD = HD + 4, TILE = AM_T * LD, ND = HD / 8;
   extern __shared__ __align__(16) float am_sm[];
   float* Ks = am_sm;              // [64][LD] resident
@@ -413,10 +479,10 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dkv_ker
     float* Qn = QD + stage * 2 * TILE;
     am_load_tile<HD>(Qn, qb, a.ldq, it * AM_T, a.Tq);
     am_load_tile<HD>(Qn + TILE, dob, a.lddo, it * AM_T, a.Tq);
-    if (threadIdx.x < AM_T) {
-      const int qi = it * AM_T + threadIdx.x;
-      LS[stage * 128 + threadIdx.x] = qi < a.Tq ? lseb[qi] : 0.f;
-      LS[stage * 128 + 64 + threadIdx.x] = qi < a.Tq ? dvb_[qi] : 0.f;
+    for (int x = threadIdx.x; x < AM_T; x += blockDim.x) {
+      const int qi = it * AM_T + x;
+      LS[stage * 128 + x] = qi < a.Tq ? lseb[qi] : 0.f;
+      LS[stage * 128 + 64 + x] = qi < a.Tq ? dvb_[qi] : 0.f;
     }
   };
   am_load_tile<HD>(Ks, kb, a.ldk, j0, a.Tk);
@@ -424,13 +490,21 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dkv_ker
   if (it0 < nit) load_q(0, it0);
   am_commit();
 
-  const int r0 = j0 + warp * 16 + g, r1 = r0 + 8;   // keys of this thread's two rows
-  const int lim0 = am_row_limit<false>(a, r0), lim1 = am_row_limit<false>(a, r1);
-  float dk[ND][4], dv[ND][4];
+  const int wrow = warp * 16 * MT;
+  int row[MT][2], lim[MT][2];   // keys of this thread's rows
+  float dk[MT][ND][4], dv[MT][ND][4];
 #pragma unroll
-  for (int dt = 0; dt < ND; ++dt) {
-    dk[dt][0] = dk[dt][1] = dk[dt][2] = dk[dt][3] = 0.f;
-    dv[dt][0] = dv[dt][1] = dv[dt][2] = dv[dt][3] = 0.f;
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      row[mt][rr] = j0 + wrow + mt * 16 + g + 8 * rr;
+      lim[mt][rr] = am_row_limit<false>(a, row[mt][rr]);
+    }
+#pragma unroll
+    for (int dt = 0; dt < ND; ++dt) {
+      dk[mt][dt][0] = dk[mt][dt][1] = dk[mt][dt][2] = dk[mt][dt][3] = 0.f;
+      dv[mt][dt][0] = dv[mt][dt][1] = dv[mt][dt][2] = dv[mt][dt][3] = 0.f;
+    }
   }
   for (int it = it0; it < nit; ++it) {
     const int st = (it - it0) & 1;
@@ -445,43 +519,50 @@ __global__ void __launch_bounds__(AM_THREADS, HD == 32 ? 3 : 2) attn_mma_dkv_ker
       am_wait0();
     }
     __syncthreads();
-    float s[8][4], dp[8][4];
+    float s[MT][8][4], dp[MT][8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-    }
-    am_prod_nt<HD, PASSES>(s, Ks + warp * 16 * LD, Qs, g, q);      // S^T[key][query]
-    am_finish_scores<false>(s, a, b, r0, r1, lim0, lim1, it * AM_T, q);
-    am_prod_nt<HD, PASSES>(dp, Vs + warp * 16 * LD, dOs, g, q);    // dP^T[key][query]
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int col = nt * 8 + 2 * q + (c & 1);
-        const float p = ex2_ftz(s[nt][c] - ls[col]);             // queries past Tq and masked entries: s = -inf -> 0
-        s[nt][c] = p;
-        dp[nt][c] = p * (dp[nt][c] - ls[64 + col]) * a.scale;
+      for (int nt = 0; nt < 8; ++nt) {
+        s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
+        dp[mt][nt][0] = dp[mt][nt][1] = dp[mt][nt][2] = dp[mt][nt][3] = 0.f;
       }
-    am_prod_acc<HD, PASSES>(dv, s, dOs, g, q);    // dV[key] += sum_i P[i][key] dO[i]
-    am_prod_acc<HD, PASSES>(dk, dp, Qs, g, q);    // dK[key] += sum_i dS[i][key] Q[i]
+    am_prod_nt<HD, PASSES, MT>(s, Ks + wrow * LD, Qs, g, q);      // S^T[key][query]
+    am_prod_nt<HD, PASSES, MT>(dp, Vs + wrow * LD, dOs, g, q);    // dP^T[key][query]
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      am_finish_scores<false>(s[mt], a, b, row[mt][0], row[mt][1], lim[mt][0], lim[mt][1], it * AM_T, q);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = nt * 8 + 2 * q + (c & 1);
+          const float p = ex2_ftz(s[mt][nt][c] - ls[col]);           // queries past Tq and masked entries: s = -inf -> 0
+          s[mt][nt][c] = p;
+          dp[mt][nt][c] = p * (dp[mt][nt][c] - ls[64 + col]) * a.scale;
+        }
+    }
+    am_prod_acc<HD, PASSES, MT>(dv, s, dOs, g, q);    // dV[key] += sum_i P[i][key] dO[i]
+    am_prod_acc<HD, PASSES, MT>(dk, dp, Qs, g, q);    // dK[key] += sum_i dS[i][key] Q[i]
     __syncthreads();
   }
   am_wait0();   // (no query tile sees this key tile: the K / V loads are still in flight)
   float* dkb = a.dk + (size_t)b * a.Tk * a.lddk + h * HD;
   float* dvb = a.dv + (size_t)b * a.Tk * a.lddv + h * HD;
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int kj = rr ? r1 : r0;
-    if (kj >= a.Tk) continue;
-    float* rk = dkb + (size_t)kj * a.lddk + 2 * q;
-    float* rv = dvb + (size_t)kj * a.lddv + 2 * q;
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int dt = 0; dt < ND; ++dt) {
-      *reinterpret_cast<float2*>(rk + dt * 8) = make_float2(dk[dt][rr * 2], dk[dt][rr * 2 + 1]);
-      *reinterpret_cast<float2*>(rv + dt * 8) = make_float2(dv[dt][rr * 2], dv[dt][rr * 2 + 1]);
+    for (int rr = 0; rr < 2; ++rr) {
+      const int kj = row[mt][rr];
+      if (kj >= a.Tk) continue;
+      float* rk = dkb + (size_t)kj * a.lddk + 2 * q;
+      float* rv = dvb + (size_t)kj * a.lddv + 2 * q;
+#pragma unroll
+      for (int dt = 0; dt < ND; ++dt) {
+        *reinterpret_cast<float2*>(rk + dt * 8) = make_float2(dk[mt][dt][rr * 2], dk[mt][dt][rr * 2 + 1]);
+        *reinterpret_cast<float2*>(rv + dt * 8) = make_float2(dv[mt][dt][rr * 2], dv[mt][dt][rr * 2 + 1]);
+      }
     }
-  }
 }
 
 template <int HD>
@@ -491,24 +572,29 @@ constexpr size_t am_dq_smem() { return sizeof(float) * 6 * AM_T * (HD + 4); }
 template <int HD>
 constexpr size_t am_dkv_smem() { return sizeof(float) * (6 * AM_T * (HD + 4) + 256); }
 
+// m-tiles per warp of the three kernels (register budget: the backward kernels hold two 16 MT x 64 blocks)
+template <int HD> constexpr int am_mt_fwd() { return AM_MT_FWD; }
+template <int HD> constexpr int am_mt_bwd() { return HD == 32 ? AM_MT_BWD32 : 1; }
+
 template <int HD, int PASSES>
 static int attn_mma_launch_t(const AttnArgs& a, int backward, cudaStream_t stream) {
+  constexpr int MF = am_mt_fwd<HD>(), MB = am_mt_bwd<HD>();
   static bool attr_set = false;
   if (!attr_set) {
-    MRG_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_fwd_kernel<HD, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)am_fwd_smem<HD>()));
-    MRG_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_dq_kernel<HD, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)am_dq_smem<HD>()));
-    MRG_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_dkv_kernel<HD, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)am_dkv_smem<HD>()));
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_fwd_kernel<HD, PASSES, MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)am_fwd_smem<HD>()));
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_dq_kernel<HD, PASSES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)am_dq_smem<HD>()));
+    MRG_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_dkv_kernel<HD, PASSES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)am_dkv_smem<HD>()));
     attr_set = true;
   }
   const dim3 gq((a.Tq + AM_T - 1) / AM_T, a.B * a.nh), gk((a.Tk + AM_T - 1) / AM_T, a.B * a.nh);
   if (!backward) {
     count_launch();
-    attn_mma_fwd_kernel<HD, PASSES><<<gq, AM_THREADS, am_fwd_smem<HD>(), stream>>>(a);
+    attn_mma_fwd_kernel<HD, PASSES, MF><<<gq, am_threads(MF), am_fwd_smem<HD>(), stream>>>(a);
   } else {
     count_launch(2);
-    attn_mma_dq_kernel<HD, PASSES><<<gq, AM_THREADS, am_dq_smem<HD>(), stream>>>(a);
+    attn_mma_dq_kernel<HD, PASSES, MB><<<gq, am_threads(MB), am_dq_smem<HD>(), stream>>>(a);
     MRG_CUDA_CHECK(cudaGetLastError());
-    attn_mma_dkv_kernel<HD, PASSES><<<gk, AM_THREADS, am_dkv_smem<HD>(), stream>>>(a);
+    attn_mma_dkv_kernel<HD, PASSES, MB><<<gk, am_threads(MB), am_dkv_smem<HD>(), stream>>>(a);
   }
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;
