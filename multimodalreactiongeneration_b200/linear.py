@@ -127,8 +127,34 @@ class _LinearFn(torch.autograd.Function):
                 _gemm(dy2, N, 1, w, K, 1, None, dx, M, K, N, ctx.flags)
             dx = dx.view(*dy.shape[:-1], K)
         wp, bp = ctx.params
+        # Only dX feeds the layer below.  Inside the trainer's backward (lstm.wgrad_overlap) the weight / bias gradients
+        # that go straight into the flat bucket are queued on the side stream of the weight-gradient GEMMs, where they run
+        # beside the next kernels of the chain instead of delaying them; the trainer joins that stream before the
+        # all-reduce / optimizer (lstm.join_wgrad_streams).
+        from . import lstm as _lstm
+        w_tgt = fused_grad_target(wp) if ctx.needs_input_grad[1] else None
+        b_tgt = fused_grad_target(bp) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        if (_lstm._WGRAD["on"] and M > 0 and w_tgt is not None
+                and (b_tgt is not None or not (ctx.has_bias and ctx.needs_input_grad[2]))):
+            dev = dy.device
+            main = torch.cuda.current_stream(dev)
+            side = _lstm._wgrad_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.device(dev), torch.cuda.stream(side):
+                _gemm(dy2, 1, N, x2, K, 1, None, w_tgt, N, K, M, ctx.flags, accumulate=1)
+                if b_tgt is not None:
+                    _colsum(dy2, into=b_tgt)
+            for t in (dy2, x2):   # the allocator must not hand these out again before the side stream is done
+                t.record_stream(side)
+            # ... and autograd must not ACCUMULATE IN PLACE into the gradient this view aliases (it does when the storage
+            # has no other owner — e.g. the residual branch adding its gradient to the same tensor): keep the view alive
+            # until the trainer has joined the side stream
+            _lstm._WGRAD["keepalive"].append(dy2)
+            if all(side != s_ for s_ in _lstm._WGRAD["pending"]):
+                _lstm._WGRAD["pending"].append(side)
+            return dx, None, None
         if ctx.needs_input_grad[1]:
-            tgt = fused_grad_target(wp)
+            tgt = w_tgt
             if tgt is not None:   # accumulate into the flat bucket, nothing for autograd to add
                 if M > 0:
                     _gemm(dy2, 1, N, x2, K, 1, None, tgt, N, K, M, ctx.flags, accumulate=1)
@@ -138,8 +164,7 @@ class _LinearFn(torch.autograd.Function):
                 if M > 0:   # dW[N,K] = dyᵀ[N,M] · x[M,K]
                     _gemm(dy2, 1, N, x2, K, 1, None, dw, N, K, M, ctx.flags)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            tgt = fused_grad_target(bp)
-            db = _colsum(dy2, into=tgt)
+            db = _colsum(dy2, into=b_tgt)
         return dx, dw, db
 
 

@@ -93,7 +93,7 @@ def set_precision(mode: str) -> None:
 # two weight-gradient GEMMs on a side stream, where they share the GPU with that next BPTT kernel (a cluster kernel leaves
 # 28 SMs idle) instead of delaying it.  Only when the gradients go straight into the trainer's flat bucket (nobody reads
 # them before the join at the end of the context).
-_WGRAD = {"on": False, "pending": [], "streams": {}}
+_WGRAD = {"on": False, "pending": [], "streams": {}, "keepalive": []}
 
 
 def _wgrad_stream(dev: torch.device) -> torch.cuda.Stream:
@@ -121,6 +121,7 @@ def join_wgrad_streams() -> None:
         if cur != side:
             cur.wait_stream(side)
     _WGRAD["pending"] = []
+    _WGRAD["keepalive"] = []
 
 
 class wgrad_overlap:
