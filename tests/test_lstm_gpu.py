@@ -197,6 +197,45 @@ def test_strided_gemm_all_majors(a_mn, b_mn, M, N, K, deint):
         assert rel_err(c.cpu(), ref) <= (2e-6 if flags == _cabi.F_SIMT_GEMM else 5e-6), (flags, a_mn, b_mn)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,acc,flags", [(19200, 1024, 256, 0, 0), (19200, 256, 1024, 1, 0), (4100, 260, 36, 0, 0),
+                                             (5000, 320, 200, 1, 0), (4096, 512, 128, 0, 32)])
+def test_presplit_weight_gemm(a_mn, b_mn, M, N, K, acc, flags):
+    """mrg_split_tf32 + mrg_gemm_strided_split (the persistent 128 x 256 kernel, csrc/mrg_gemm_tc4.cu) against fp64 for
+    every operand major, ragged M / N / K (TMA zero fill, guarded epilogue), bias, accumulate, and the one-pass mode;
+    the split planes themselves are exact: hi + lo == w bit for bit, hi has a 10-bit mantissa."""
+    from multimodalreactiongeneration_b200 import _cabi
+    L = _cabi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(6)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ Bm.double() + bias.double() + (c0.double() if acc else 0)
+    a_dev = (A.t().contiguous() if a_mn else A.contiguous()).cuda()
+    b_dev = (Bm.contiguous() if b_mn else Bm.t().contiguous()).cuda()
+    a_sm, a_sk = (1, M) if a_mn else (K, 1)
+    b_sk, b_sn = (N, 1) if b_mn else (1, K)
+    hl = torch.empty((2,) + tuple(b_dev.shape), device="cuda")
+    _cabi.check(L.mrg_split_tf32(b_dev.data_ptr(), hl[0].data_ptr(), hl[1].data_ptr(), b_dev.numel(), st), "mrg_split_tf32")
+    assert torch.equal(hl[0] + hl[1], b_dev)
+    assert int((hl[0].view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert L.mrg_gemm_split_supported(M, N, K, a_sm, a_sk, b_sk, b_sn, N) == 1
+    c = c0.clone().cuda()
+    _cabi.check(L.mrg_gemm_strided_split(a_dev.data_ptr(), a_sm, a_sk, hl[0].data_ptr(), hl[1].data_ptr(), b_sk, b_sn,
+                                         bias.cuda().data_ptr(), c.data_ptr(), N, M, N, K, acc, None, 0, flags, st),
+                "mrg_gemm_strided_split")
+    torch.cuda.synchronize()
+    # 3xTF32 with one accumulation chain over K (no split-K): the tensor core's fp32 accumulation truncates, the error
+    # grows with K (measured 2e-6 at K = 256, 9e-6 at K = 1024)
+    assert rel_err(c.cpu(), ref) <= (2e-3 if flags else (5e-6 if K <= 256 else 1.5e-5))
+    # shapes the kernel does not cover are refused loudly (the caller keeps the unsplit path)
+    assert L.mrg_gemm_split_supported(64, N, K, a_sm, a_sk, b_sk, b_sn, N) == 0
+    assert L.mrg_gemm_strided_split(a_dev.data_ptr(), a_sm, a_sk, hl[0].data_ptr(), hl[1].data_ptr(), b_sk, b_sn, None,
+                                    c.data_ptr(), N, 64, N, K, 0, None, 0, 0, st) != 0
+
+
 @pytest.mark.parametrize("H,bi", [(256, False), (32, True)])
 def test_single_step_zero_state_pointwise_path(H, bi):
     """T == 1 with hx=None takes the pointwise cell kernels (no recurrence); must equal torch.nn.LSTM."""
