@@ -16,12 +16,15 @@
 //    128 x 256 x 32 k-block: 16 KB (A in) + 16 KB (A converter reads) + 64 KB (B in) + 96 KB (MMA operand reads)
 //    = 192 KB = 1500 cycles at 128 B/clk against 1536 cycles of MMA;
 //  * keeps the A path of the second generation: raw fp32 (or bfloat16) tile by TMA, converter warps split it in registers
-//    and write hi | lo into tensor memory, the MMAs take A from TMEM (.ts form) — 2 shared-memory stages (free again as
-//    soon as the converter has read them) feeding 3 tensor-memory stages, decoupled from the 3 B stages;
+//    and write hi | lo into tensor memory, the MMAs take A from TMEM (.ts form) — 3 shared-memory stages (free again as
+//    soon as the converter has read them) feeding 3 tensor-memory stages, decoupled from the 2 B stages (64 KB each; a
+//    third does not fit beside the epilogue's transpose buffers — the hi / lo barrier split below hides that);
 //  * drains the accumulator in one go: every epilogue thread pulls its 128 columns into registers (setmaxnreg moves
-//    registers from the producer / MMA warps to the epilogue warps), hands the accumulator back to the MMA issuer and only
-//    then adds the bias and stores — the first version held the accumulator through the global stores, ~5900 cycles per
-//    tile with every SM writing at once (profiles/r2_gemm_tc4_trace.txt).
+//    registers from the producer / MMA warps to the epilogue warps), hands the accumulator back to the MMA issuer ~300
+//    cycles after the last MMA and only then adds the bias and stores through a per-warp shared-memory transpose (full
+//    128-byte row segments per store instruction) — the first version held the accumulator through the global stores,
+//    ~5900 cycles per tile with every SM writing at once; storing 16 bytes per lane straight from the registers was
+//    slower still (profiles/r2_gemm_tc4_trace.txt, r2_gemm_split_check.txt).
 // Same arithmetic as the 128 x 128 kernel: D += A_lo B_hi + A_hi B_lo + A_hi B_hi per k-step, fp32 accumulation in TMEM.
 //
 // Tiles are handed out DYNAMICALLY (warp 2: atomic counter -> 4-deep shared-memory ring -> every role): the step runs
