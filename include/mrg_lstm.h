@@ -132,6 +132,11 @@ int mrg_gemm_strided(const float* a, long long a_sm, long long a_sk, const float
                      void* stream);
 size_t mrg_gemm_workspace_bytes(int M, int N, int K);
 
+/* dst[n0][n1][H] (contiguous) = src[i0 * s0 + i1 * s1 + h]: the batch-first <-> time-major relayout of a [B, T, H] activation
+ * in front of / behind a layer (B200LSTM takes time-major input; the reference's tensors are batch_first).  H % 4 == 0,
+ * strides multiples of 4 floats, 16-byte aligned pointers. */
+int mrg_copy_rows(const float* src, long long s0, long long s1, float* dst, int n0, int n1, int H, void* stream);
+
 /* Weight operand split once: hi[i] = w[i] rounded to tf32 (nearest, ties away), lo[i] = w[i] - hi[i] (exact).
  * mrg_gemm_strided_split is mrg_gemm_strided (no de-interleave) with B given as those two planes: it runs the persistent
  * 128 x 256 tcgen05 kernel (csrc/mrg_gemm_tc4.cu), which needs no B conversion pass.  Covered shapes:

@@ -23,7 +23,7 @@ EXPORTS = (
     "mrg_attention_forward", "mrg_attention_backward", "mrg_gru_forward", "mrg_gru_backward",
     "mrg_rollout_supported", "mrg_rollout_forward", "mrg_rollout_backward", "mrg_profile_kernel_name",
     "mrg_lstm_pack_floats", "mrg_split_tf32", "mrg_gemm_split_supported", "mrg_gemm_strided_split",
-    "mrg_audio_features", "mrg_attention_set_mode",
+    "mrg_audio_features", "mrg_attention_set_mode", "mrg_copy_rows",
 )
 
 
@@ -109,6 +109,8 @@ def lib() -> ctypes.CDLL:
     L.mrg_audio_features.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, LL, LL, c_int,
                                      c_int, c_int, c_int, c_void_p]
     L.mrg_audio_features.restype = c_int
+    L.mrg_copy_rows.argtypes = [c_void_p, LL, LL, c_void_p, c_int, c_int, c_int, c_void_p]
+    L.mrg_copy_rows.restype = c_int
     L.mrg_gemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.mrg_gemm_workspace_bytes.restype = c_size_t
     L.mrg_layernorm_workspace_bytes.argtypes = [c_int]
@@ -159,6 +161,8 @@ def lib() -> ctypes.CDLL:
     L.mrg_profile_kernel_name.argtypes = [c_int]
     L.mrg_profile_kernel_name.restype = c_char_p
     _LIB = L
+    if os.environ.get("MRG_PRECISION", "fp32") in ("tf32", "bf16"):   # reduced-precision mode chosen by the environment:
+        L.mrg_attention_set_mode(1)                                      # the attention kernels run one tf32 pass too
     return L
 
 
@@ -188,6 +192,25 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = lib().mrg_last_error_string().decode("utf-8", "replace")
         raise MrgError(f"{what} failed with status {status}: {msg}")
+
+
+def contiguous3(t):
+    """``t.contiguous()`` for a 3-D fp32 CUDA tensor whose rows (last dimension) are contiguous — the transposed views at
+    the LSTM seam — through ``mrg_copy_rows`` (a row copy at HBM speed; torch's generic strided copy is ~6x slower on
+    these shapes).  Anything else goes to torch."""
+    if t.is_contiguous():
+        return t
+    if (t.dim() == 3 and t.is_cuda and t.dtype.is_floating_point and t.element_size() == 4 and t.stride(2) == 1
+            and t.shape[2] % 4 == 0 and t.stride(0) % 4 == 0 and t.stride(1) % 4 == 0 and t.data_ptr() % 16 == 0
+            and t.numel() > 0):
+        import torch
+        out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        with torch.cuda.device(t.device):
+            st = lib().mrg_copy_rows(t.data_ptr(), t.stride(0), t.stride(1), out.data_ptr(), t.shape[0], t.shape[1],
+                                     t.shape[2], torch.cuda.current_stream(t.device).cuda_stream)
+        check(st, "mrg_copy_rows")
+        return out
+    return t.contiguous()
 
 
 def ptr(t) -> int | None:

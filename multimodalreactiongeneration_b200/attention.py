@@ -52,7 +52,7 @@ class AttentionMaskSpec:
 def _rows(t: torch.Tensor):
     """[B, T, C] view whose rows are contiguous and whose batch stride is T * row stride -> (tensor, row stride)."""
     if t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1) or t.stride(1) % 4 or t.data_ptr() % 16:
-        t = t.contiguous()
+        t = _cabi.contiguous3(t) if t.dim() == 3 else t.contiguous()
     return t, t.stride(1)
 
 

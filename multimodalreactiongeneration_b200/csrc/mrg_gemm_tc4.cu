@@ -479,9 +479,9 @@ int gemm_tc4(const GemmArgs& g, cudaStream_t stream) {
   static int sms = 0;
   if (sms == 0) {
     MRG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM4_BYTES));
-    int dev = 0;
-    MRG_CUDA_CHECK(cudaGetDevice(&dev));
-    MRG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int dev0 = 0;
+    MRG_CUDA_CHECK(cudaGetDevice(&dev0));
+    MRG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev0));
   }
   CUtensorMap ma, mbh, mbl;
   TcParams p = {};
@@ -500,10 +500,13 @@ int gemm_tc4(const GemmArgs& g, cudaStream_t stream) {
   Tc4Work w;
   w.tiles_n = (g.N + NT4 - 1) / NT4;
   w.items = w.tiles_n * ((g.M + TBM - 1) / TBM);
-  static unsigned int* counters = nullptr;
-  static std::atomic<unsigned int> seq{0};   // one device per process (the trainer's model)
-  if (!counters) MRG_CUDA_CHECK(cudaGetSymbolAddress((void**)&counters, g_tc4_counters));
-  w.counter = counters + 2 * (seq.fetch_add(1) % TC4_SLOTS);
+  static unsigned int* counters_of[64] = {};   // the symbol has one instance per device
+  static std::atomic<unsigned int> seq{0};
+  int dev = 0;
+  MRG_CUDA_CHECK(cudaGetDevice(&dev));
+  MRG_REQUIRE(dev >= 0 && dev < 64, "gemm_tc4: device index %d out of range", dev);
+  if (!counters_of[dev]) MRG_CUDA_CHECK(cudaGetSymbolAddress((void**)&counters_of[dev], g_tc4_counters));
+  w.counter = counters_of[dev] + 2 * (seq.fetch_add(1) % TC4_SLOTS);
   ProfScope prof(PROF_GEMM, stream);
   count_launch();
   gemm_tc4_kernel<<<w.items < sms ? w.items : sms, TC4_THREADS, SMEM4_BYTES, stream>>>(ma, mbh, mbl, p, w);

@@ -96,6 +96,20 @@ int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack,
   return 0;
 }
 
+// dst[i0][i1][0..H) (contiguous) = src[i0 * s0 + i1 * s1 + ..]: the batch-first <-> time-major relayout in front of / behind
+// an LSTM layer as a row copy (every row is H contiguous floats on both sides; 16-byte accesses, grid-stride)
+__global__ void copy_rows_kernel(const float* __restrict__ src, long long s0, long long s1, float* __restrict__ dst, int n0,
+                                 int n1, int H4) {
+  const long long total = (long long)n0 * n1 * H4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % H4);
+    const long long r = i / H4;
+    const int i1 = (int)(r % n1);
+    const long long i0 = r / n1;
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src + i0 * s0 + i1 * s1) + c);
+  }
+}
+
 __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = w[i];
@@ -106,6 +120,20 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
 }
 
 }  // namespace mrg
+extern "C" int mrg_copy_rows(const float* src, long long s0, long long s1, float* dst, int n0, int n1, int H, void* stream) {
+  MRG_REQUIRE(src && dst && n0 >= 0 && n1 >= 0 && H > 0 && H % 4 == 0 && s0 % 4 == 0 && s1 % 4 == 0 &&
+                  (((uintptr_t)src | (uintptr_t)dst) & 15) == 0,
+              "mrg_copy_rows: rows of H %% 4 == 0 floats, 16-byte aligned, strides multiples of 4");
+  const long long total = (long long)n0 * n1 * (H / 4);
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mrg::copy_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, s0, s1, dst, n0, n1, H / 4);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  mrg::count_launch();
+  return 0;
+}
+
 extern "C" int mrg_split_tf32(const float* w, float* hi, float* lo, size_t n, void* stream) {
   MRG_REQUIRE(w && hi && lo, "mrg_split_tf32: null pointer");
   if (n == 0) return 0;

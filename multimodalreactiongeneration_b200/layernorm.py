@@ -25,7 +25,7 @@ def _dense3(t: torch.Tensor) -> torch.Tensor:
     ok = t.stride(-1) == 1 and t.stride(0) % 4 == 0 and t.stride(1) % 4 == 0 and t.data_ptr() % 16 == 0
     if ok and (t.is_contiguous() or t.transpose(0, 1).is_contiguous()):
         return t
-    return t.contiguous()
+    return _cabi.contiguous3(t)
 
 
 class _ResidualLNFn(torch.autograd.Function):

@@ -91,7 +91,7 @@ class _LinearFn(torch.autograd.Function):
         if x.dtype != torch.float32 or weight.dtype != torch.float32:
             raise TypeError("B200Linear computes in fp32")
         N, K = weight.shape
-        x2 = x.reshape(-1, K).contiguous()
+        x2 = (_cabi.contiguous3(x) if x.dim() == 3 else x).reshape(-1, K).contiguous()
         M = x2.shape[0]
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         flags = _default_flags()
@@ -116,7 +116,7 @@ class _LinearFn(torch.autograd.Function):
         x2, weight = ctx.saved_tensors
         N, K = weight.shape
         M = x2.shape[0]
-        dy2 = dy.reshape(-1, N).contiguous()
+        dy2 = (_cabi.contiguous3(dy) if dy.dim() == 3 else dy).reshape(-1, N).contiguous()
         dx = dw = db = None
         w = weight.contiguous()
         if ctx.needs_input_grad[0]:

@@ -147,7 +147,7 @@ class _LSTMLayerFn(torch.autograd.Function):
             raise RuntimeError("B200LSTM has no CPU path: inputs must live on a B200 (sm_100a) device")
         if x.dtype != torch.float32:
             raise TypeError(f"B200LSTM computes in fp32; got {x.dtype}")
-        x = x.contiguous()
+        x = _cabi.contiguous3(x)
         T, B, I = x.shape
         dev = x.device
         need_grad = any(ctx.needs_input_grad)
@@ -206,7 +206,7 @@ class _LSTMLayerFn(torch.autograd.Function):
         T, B, I, H, D, flags = ctx.dims
         dev = x.device
         opts = dict(dtype=torch.float32, device=dev)
-        dy = None if dy is None else dy.contiguous()
+        dy = None if dy is None else _cabi.contiguous3(dy)
         dh_n = None if dh_n is None else dh_n.contiguous()
         dc_n = None if dc_n is None else dc_n.contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None

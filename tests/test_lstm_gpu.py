@@ -400,3 +400,19 @@ def test_cluster_budget_gives_identical_results(budget):
     for a, b_ in zip(*outs[:2]):
         assert torch.equal(a, b_) or rel_err(a, b_) <= 1e-6
     assert torch.equal(outs[0][0], outs[1][0])   # the forward is bit-identical
+
+
+def test_copy_rows_equals_contiguous():
+    """mrg_copy_rows (the batch-first <-> time-major relayout at the LSTM seam) is bit-exact against torch's copy for
+    transposed and sliced 3-D views, and contiguous3 leaves shapes it does not cover to torch."""
+    from multimodalreactiongeneration_b200 import _cabi
+    g = torch.Generator().manual_seed(21)
+    base = torch.randn(37, 19, 256, generator=g).cuda()
+    for view in (base.transpose(0, 1), base[:, 3:11], base.transpose(0, 1)[2:9, ::2], base[..., :128].transpose(0, 1)):
+        assert not view.is_contiguous()
+        got = _cabi.contiguous3(view)
+        assert got.is_contiguous() and torch.equal(got, view.contiguous())
+    odd = torch.randn(5, 7, 6, generator=g).cuda().transpose(0, 1)     # rows of 6 floats: torch's path
+    assert torch.equal(_cabi.contiguous3(odd), odd.contiguous())
+    same = torch.randn(4, 4, 8).cuda()
+    assert _cabi.contiguous3(same) is same
