@@ -112,7 +112,7 @@ def note_fused_write(dev: torch.device) -> None:
         _WGRAD["pending"].append(st)
 
 
-def join_wgrad_streams() -> None:
+def join_wgrad_streams(final: bool = False) -> None:
     """The current stream waits for every stream that has queued a write into the flat gradient bucket so far:
     the side streams of the weight-gradient GEMMs and any stream a fused weight-gradient kernel ran on (e.g. the
     second encoder stream of SimpleLSTM) — an explicit join, not the autograd engine's leaf-stream sync."""
@@ -121,7 +121,8 @@ def join_wgrad_streams() -> None:
         if cur != side:
             cur.wait_stream(side)
     _WGRAD["pending"] = []
-    _WGRAD["keepalive"] = []
+    if final:   # end of the backward: no gradient accumulation of autograd is outstanding any more
+        _WGRAD["keepalive"] = []
 
 
 class wgrad_overlap:
@@ -132,7 +133,7 @@ class wgrad_overlap:
 
     def __exit__(self, *exc):
         _WGRAD["on"] = self.prev
-        join_wgrad_streams()
+        join_wgrad_streams(final=True)
         return False
 
 
