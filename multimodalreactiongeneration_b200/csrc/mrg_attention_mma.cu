@@ -62,8 +62,8 @@ __device__ __forceinline__ void am_prod_nt(float (&c)[MT][8][4], const float* X,
       const float* yr = Y + (nt * 8 + g) * LD + ks * 8 + q;
       y0[nt] = yr[0];
       y1[nt] = yr[4];
-      h0[nt] = tf32_rna(y0[nt]);
-      h1[nt] = tf32_rna(y1[nt]);
+      h0[nt] = am_hi<PASSES>(y0[nt]);
+      h1[nt] = am_hi<PASSES>(y1[nt]);
     }
     if (PASSES == 3) {
 #pragma unroll
@@ -106,8 +106,8 @@ __device__ __forceinline__ void am_prod_acc(float (&o)[MT][HD / 8][4], const flo
     for (int dt = 0; dt < HD / 8; ++dt) {
       y0[dt] = yp[dt * 8];
       y1[dt] = yp[LD + dt * 8];
-      h0[dt] = tf32_rna(y0[dt]);
-      h1[dt] = tf32_rna(y1[dt]);
+      h0[dt] = am_hi<PASSES>(y0[dt]);
+      h1[dt] = am_hi<PASSES>(y1[dt]);
     }
     if (PASSES == 3) {
 #pragma unroll

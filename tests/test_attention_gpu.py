@@ -73,6 +73,44 @@ def test_fused_attention_matches_fp64_reference(B, nh, hd, Tq, Tk, mode, rate, p
     assert rel_l2(got[2][..., E:], kv64.grad[..., E:].cpu()) <= 1e-4
 
 
+@pytest.mark.parametrize("mode,out_tol,grad_tol", [(1, 5e-3, 2e-2), (2, 1e-5, 1e-4)])
+def test_attention_modes(mode, out_tol, grad_tol):
+    """mrg_attention_set_mode: 1 = one tf32 pass (the tf32 / bf16 precision modes; stated bound of those modes) — must
+    differ from the 3xTF32 default, i.e. the switch is honoured; 2 = the CUDA-core fp32 kernels (cross-check path) at the
+    fp32-grade tolerance.  Causal + padded lstmformer shape."""
+    from multimodalreactiongeneration_b200 import _cabi
+    from multimodalreactiongeneration_b200.attention import AttentionMaskSpec, fused_attention
+    B, nh, hd, T = 2, 4, 64, 200
+    E = nh * hd
+    g = torch.Generator().manual_seed(17)
+    q0 = torch.randn(B, T, E, generator=g).cuda()
+    kv0 = torch.randn(B, T, 2 * E, generator=g).cuda()
+    w = torch.randn(B, T, E, generator=g).cuda()
+    pad = torch.zeros(B, T, dtype=torch.uint8)
+    pad[0, T - 30:] = 1
+    spec = AttentionMaskSpec(1, 1, pad.cuda(), pad.cuda())
+
+    def run():
+        q, kv = q0.clone().requires_grad_(True), kv0.clone().requires_grad_(True)
+        out = fused_attention(q, kv, None, nh, spec)
+        (out * w).sum().backward()
+        return out.detach().cpu(), q.grad.cpu(), kv.grad.cpu()
+
+    base = run()
+    try:
+        _cabi.check(_cabi.lib().mrg_attention_set_mode(mode), "mrg_attention_set_mode")
+        got = run()
+    finally:
+        _cabi.lib().mrg_attention_set_mode(0)
+    q64, kv64 = q0.double().cpu().requires_grad_(True), kv0.double().cpu().requires_grad_(True)
+    ref = _reference(q64, kv64[..., :E], kv64[..., E:], nh, spec.materialize(nh).cpu())
+    (ref * w.double().cpu()).sum().backward()
+    assert rel_err(got[0], ref.detach()) <= out_tol
+    assert rel_l2(got[1], q64.grad) <= grad_tol and rel_l2(got[2], kv64.grad) <= grad_tol
+    if mode == 1:
+        assert rel_err(got[0], base[0]) > 1e-5   # really one pass
+
+
 def test_mask_rule_equals_the_reference_mask_tensor():
     """AttentionMaskSpec.materialize == the tile / transpose construction of the reference (restated here)."""
     from multimodalreactiongeneration_b200.attention import AttentionMaskSpec
