@@ -172,7 +172,12 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   r.cluster_budget = (flags >> 16) & 0xFF;
   r.bf16_gates = bf16 ? 1 : 0;
   r.gru = gru ? 1 : 0;
-  if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) return rec_forward_cluster2(r, stream);
+  if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) {
+    int sl3 = 0, nc3 = 0;   // reduced-precision modes with many rows per cluster: h W_hh^T on the tensor cores
+    if ((flags & (MRG_F_TF32 | MRG_F_BF16)) && rec_forward_mma_applies(r, &sl3, &nc3))
+      return rec_forward_cluster3(r, sl3, nc3, stream);
+    return rec_forward_cluster2(r, stream);
+  }
   return rec_forward_generic(r, stream);
 }
 

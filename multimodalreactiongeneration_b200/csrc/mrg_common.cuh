@@ -310,6 +310,9 @@ int rec_backward_generic(const RecBwdArgs& a, cudaStream_t stream);
 int rec_forward_cluster2(const RecArgs& a, cudaStream_t stream);
 int rec_backward_cluster2(const RecBwdArgs& a, cudaStream_t stream);
 bool rec2_supported(int H);
+// tensor-core forward recurrence of the reduced-precision modes (mrg_rec_fwd3.cu)
+bool rec_forward_mma_applies(const RecArgs& a, int* slices, int* nch);
+int rec_forward_cluster3(const RecArgs& a, int slices, int nch, cudaStream_t stream);
 int max_active_clusters2(int H);
 int rec2_max_chunks(int H, int rbc);
 void pick_partition2(int H, int B, int D, int budget, int* slices_out, int* nch_out, int* rbc_out);

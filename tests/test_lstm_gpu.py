@@ -356,6 +356,49 @@ def test_bf16_mode_within_stated_bound(I, H, L, bi, B, T):
         assert rel_l2(pm.grad.cpu(), pr.grad) <= BF16_GRAD_TOL, name
 
 
+@pytest.mark.parametrize("mode,B,T,L,bi,with_hx", [("bf16", 256, 40, 2, False, True), ("tf32", 130, 25, 1, False, False),
+                                                  ("bf16", 270, 12, 1, True, True), ("tf32", 600, 6, 1, False, True)])
+def test_reduced_precision_tensor_core_recurrence(mode, B, T, L, bi, with_hx):
+    """In the reduced-precision modes a cluster with >= 8 rows runs h W_hh^T on the warp-level tensor cores
+    (rec_fwd3_kernel, one tf32 pass).  Same stated bound as the modes themselves (states 2e-2 per step, gradients 5e-2)
+    against fp64 nn.LSTM: 17-18 rows per cluster in two chunks, ragged 8-9 rows, both directions, 40 rows in three
+    chunks, carried state."""
+    import multimodalreactiongeneration_b200 as pkg
+    from multimodalreactiongeneration_b200 import _cabi
+    H = 256
+    ref, mine = _build(H, H, L, bi)
+    D = 2 if bi else 1
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, T, H, generator=g, dtype=torch.double)
+    hx = None
+    if with_hx:
+        hx = (torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5,
+              torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5)
+    w = torch.randn(B, T, D * H, generator=g, dtype=torch.double)
+    xr = x.clone().requires_grad_(True)
+    yr, (hnr, cnr) = ref(xr, hx)
+    (yr * w).sum().backward()
+    _cabi.profile_enable(True)
+    try:
+        pkg.set_precision(mode)
+        xm = x.float().cuda().requires_grad_(True)
+        hm = None if hx is None else tuple(t.float().cuda() for t in hx)
+        ym, (hnm, cnm) = mine(xm, hm)
+        (ym * w.float().cuda()).sum().backward()
+        torch.cuda.synchronize()
+        name = _cabi.profile_kernel_name("rec_fwd")
+    finally:
+        pkg.set_precision("fp32")
+        _cabi.profile_read()
+        _cabi.profile_enable(False)
+    assert "rec_fwd3" in name, name          # the tensor-core kernel really ran
+    assert _per_step_err(ym, yr) <= BF16_STATE_TOL
+    assert rel_err(hnm.cpu(), hnr) <= BF16_STATE_TOL and rel_err(cnm.cpu(), cnr) <= BF16_STATE_TOL
+    assert rel_l2(xm.grad.cpu(), xr.grad) <= BF16_GRAD_TOL
+    for (pname, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        assert rel_l2(pm.grad.cpu(), pr.grad) <= BF16_GRAD_TOL, pname
+
+
 def test_bf16_mode_falls_back_to_fp32_reserve_on_generic_shapes():
     """Shapes the cluster kernels do not cover (H=32: generic kernels; T=1: pointwise cell) keep the fp32 reserve in
     bf16 mode (documented in set_precision) and stay inside the bound."""

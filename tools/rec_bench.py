@@ -35,7 +35,8 @@ if __name__ == "__main__":
               (64, 300, 128, 2), (1024, 30, 256, 1), (16, 300, 256, 1), (32, 300, 256, 1)]
     for (B, T, H, D) in shapes:
         row = f"B={B:5d} T={T} H={H} D={D}:"
-        for name, fl in (("cluster", 0),):
+        variants = (("cluster", 0),) if os.environ.get("REDUCED", "0") != "1" else (("fp32", 0), ("tf32-mode", _cabi.F_TF32))
+        for name, fl in variants:
             try:
                 f, b = run(B, T, H, D, fl)
                 row += f"  {name} fwd {f*1e3:8.1f} us ({f*1e3/T:5.2f}/step) bwd {b*1e3:8.1f} us ({b*1e3/T:5.2f}/step)"
