@@ -232,7 +232,12 @@ extern "C" int mrg_lstm_layer_backward(const float* x, const mrg_lstm_dir_weight
   for (int d = 0; d < D; ++d) pointwise = pointwise && !g[d].dh0 && !g[d].dc0;
   if (!do_rec) e = 0;
   else if (pointwise) e = cell_zero_state_backward(gates, c_ext, dy, dh_n, dc_n, db_part, B, H, D, stream);
-  else if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) e = rec_backward_cluster2(r, stream);
+  else if (!(flags & MRG_F_GENERIC_REC) && rec2_supported(H)) {
+    int sl3 = 0, nc3 = 0;   // reduced-precision modes with many rows per cluster: dpre W_hh on the tensor cores
+    if ((flags & (MRG_F_TF32 | MRG_F_BF16)) && rec_backward_mma_applies(r, &sl3, &nc3))
+      e = rec_backward_cluster3(r, sl3, nc3, stream);
+    else e = rec_backward_cluster2(r, stream);
+  }
   else e = rec_backward_generic(r, stream);
   if (e) return e;
 

@@ -313,6 +313,9 @@ bool rec2_supported(int H);
 // tensor-core forward recurrence of the reduced-precision modes (mrg_rec_fwd3.cu)
 bool rec_forward_mma_applies(const RecArgs& a, int* slices, int* nch);
 int rec_forward_cluster3(const RecArgs& a, int slices, int nch, cudaStream_t stream);
+// tensor-core BPTT of the reduced-precision modes (mrg_rec_bwd3.cu)
+bool rec_backward_mma_applies(const RecBwdArgs& a, int* slices, int* nch);
+int rec_backward_cluster3(const RecBwdArgs& a, int slices, int nch, cudaStream_t stream);
 int max_active_clusters2(int H);
 int rec2_max_chunks(int H, int rbc);
 void pick_partition2(int H, int B, int D, int budget, int* slices_out, int* nch_out, int* rbc_out);

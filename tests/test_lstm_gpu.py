@@ -359,10 +359,10 @@ def test_bf16_mode_within_stated_bound(I, H, L, bi, B, T):
 @pytest.mark.parametrize("mode,B,T,L,bi,with_hx", [("bf16", 256, 40, 2, False, True), ("tf32", 130, 25, 1, False, False),
                                                   ("bf16", 270, 12, 1, True, True), ("tf32", 600, 6, 1, False, True)])
 def test_reduced_precision_tensor_core_recurrence(mode, B, T, L, bi, with_hx):
-    """In the reduced-precision modes a cluster with >= 8 rows runs h W_hh^T on the warp-level tensor cores
-    (rec_fwd3_kernel, one tf32 pass).  Same stated bound as the modes themselves (states 2e-2 per step, gradients 5e-2)
-    against fp64 nn.LSTM: 17-18 rows per cluster in two chunks, ragged 8-9 rows, both directions, 40 rows in three
-    chunks, carried state."""
+    """In the reduced-precision modes a cluster with >= 8 rows runs h W_hh^T (rec_fwd3_kernel) and dpre W_hh
+    (rec_bwd3_kernel) on the warp-level tensor cores, one tf32 pass.  Same stated bound as the modes themselves (states
+    2e-2 per step, gradients 5e-2) against fp64 nn.LSTM: 17-18 rows per cluster in two chunks, ragged 8-9 rows, both
+    directions (39 rows, three chunks), 40 rows in three chunks, carried state with gradients at h_n / c_n and h_0 / c_0."""
     import multimodalreactiongeneration_b200 as pkg
     from multimodalreactiongeneration_b200 import _cabi
     H = 256
@@ -375,28 +375,39 @@ def test_reduced_precision_tensor_core_recurrence(mode, B, T, L, bi, with_hx):
         hx = (torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5,
               torch.randn(L * D, B, H, generator=g, dtype=torch.double) * 0.5)
     w = torch.randn(B, T, D * H, generator=g, dtype=torch.double)
+    wh = torch.randn(L * D, B, H, generator=g, dtype=torch.double)
+    wc = torch.randn(L * D, B, H, generator=g, dtype=torch.double)
     xr = x.clone().requires_grad_(True)
-    yr, (hnr, cnr) = ref(xr, hx)
-    (yr * w).sum().backward()
+    hr = None if hx is None else tuple(t.clone().requires_grad_(True) for t in hx)
+    yr, (hnr, cnr) = ref(xr, hr)
+    ((yr * w).sum() + (hnr * wh).sum() + (cnr * wc).sum()).backward()
     _cabi.profile_enable(True)
     try:
         pkg.set_precision(mode)
         xm = x.float().cuda().requires_grad_(True)
-        hm = None if hx is None else tuple(t.float().cuda() for t in hx)
+        hm = None if hx is None else tuple(t.float().cuda().requires_grad_(True) for t in hx)
         ym, (hnm, cnm) = mine(xm, hm)
-        (ym * w.float().cuda()).sum().backward()
+        ((ym * w.float().cuda()).sum() + (hnm * wh.float().cuda()).sum() + (cnm * wc.float().cuda()).sum()).backward()
         torch.cuda.synchronize()
         name = _cabi.profile_kernel_name("rec_fwd")
+        name_b = _cabi.profile_kernel_name("rec_bwd")
     finally:
         pkg.set_precision("fp32")
         _cabi.profile_read()
         _cabi.profile_enable(False)
-    assert "rec_fwd3" in name, name          # the tensor-core kernel really ran
+    assert "rec_fwd3" in name, name          # the tensor-core kernels really ran
+    assert "rec_bwd3" in name_b, name_b
     assert _per_step_err(ym, yr) <= BF16_STATE_TOL
     assert rel_err(hnm.cpu(), hnr) <= BF16_STATE_TOL and rel_err(cnm.cpu(), cnr) <= BF16_STATE_TOL
-    assert rel_l2(xm.grad.cpu(), xr.grad) <= BF16_GRAD_TOL
+    errs = {"x": rel_l2(xm.grad.cpu(), xr.grad)}
     for (pname, pr), pm in zip(ref.named_parameters(), mine.parameters()):
-        assert rel_l2(pm.grad.cpu(), pr.grad) <= BF16_GRAD_TOL, pname
+        errs[pname] = rel_l2(pm.grad.cpu(), pr.grad)
+    if hx is not None:
+        errs["h0"] = rel_l2(hm[0].grad.cpu(), hr[0].grad)
+        errs["c0"] = rel_l2(hm[1].grad.cpu(), hr[1].grad)
+    print(mode, B, T, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v <= BF16_GRAD_TOL, (k, v)
 
 
 def test_bf16_mode_falls_back_to_fp32_reserve_on_generic_shapes():

@@ -519,6 +519,47 @@ def test_gru_matches_torch_gru(I, H, L, bi, B, T, with_hx):
         assert rel_l2(hm.grad.cpu(), hr.grad) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("mode,B,T,bi", [("tf32", 256, 30, False), ("bf16", 150, 17, True)])
+def test_gru_reduced_precision_tensor_core_recurrence(mode, B, T, bi):
+    """GRU variant of the tensor-core recurrent kernels (rec_fwd3 / rec_bwd3_kernel<256, gru>) in the reduced-precision
+    modes: fp64 nn.GRU, the modes' stated bound (states 2e-2, gradients 5e-2), carried state, both directions."""
+    import multimodalreactiongeneration_b200 as pkg
+    from multimodalreactiongeneration_b200 import B200GRU, _cabi
+    H = 256
+    torch.manual_seed(19)
+    ref = torch.nn.GRU(H, H, 1, batch_first=True, bidirectional=bi).double()
+    mine = B200GRU(H, H, 1, batch_first=True, bidirectional=bi)
+    mine.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mine = mine.cuda()
+    D = 2 if bi else 1
+    g = torch.Generator().manual_seed(20)
+    x = torch.randn(B, T, H, generator=g, dtype=torch.double)
+    h0 = torch.randn(D, B, H, generator=g, dtype=torch.double) * 0.5
+    wy = torch.randn(B, T, D * H, generator=g, dtype=torch.double)
+    wh = torch.randn(D, B, H, generator=g, dtype=torch.double)
+    xr, hr = x.clone().requires_grad_(True), h0.clone().requires_grad_(True)
+    yr, hnr = ref(xr, hr)
+    ((yr * wy).sum() + (hnr * wh).sum()).backward()
+    _cabi.profile_enable(True)
+    try:
+        pkg.set_precision(mode)
+        xm, hm = x.float().cuda().requires_grad_(True), h0.float().cuda().requires_grad_(True)
+        ym, hnm = mine(xm, hm)
+        ((ym * wy.float().cuda()).sum() + (hnm * wh.float().cuda()).sum()).backward()
+        torch.cuda.synchronize()
+        names = _cabi.profile_kernel_name("rec_fwd"), _cabi.profile_kernel_name("rec_bwd")
+    finally:
+        pkg.set_precision("fp32")
+        _cabi.profile_read()
+        _cabi.profile_enable(False)
+    assert "rec_fwd3" in names[0] and "gru" in names[0], names
+    assert "rec_bwd3" in names[1] and "gru" in names[1], names
+    assert rel_err(ym.cpu(), yr) <= 2e-2 and rel_err(hnm.cpu(), hnr) <= 2e-2
+    assert rel_l2(xm.grad.cpu(), xr.grad) <= 5e-2 and rel_l2(hm.grad.cpu(), hr.grad) <= 5e-2
+    for (name, pr), pm in zip(ref.named_parameters(), mine.parameters()):
+        assert rel_l2(pm.grad.cpu(), pr.grad) <= 5e-2, name
+
+
 def test_gru_mixer_layerd_matches_reference():
     from multimodalreactiongeneration_b200.mr_gen.model.utils.mixer_block import GRUMixerLayerd
     sd, ins, outs, grads, meta = load_golden("gru_mixer_layerd")
