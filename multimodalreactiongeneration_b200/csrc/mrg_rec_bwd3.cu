@@ -290,12 +290,13 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
       const float* dr = &C.dpre[g8][4 * q];
-      const bool second = g8 + 8 < nr;   // rows past the chunk's count are zero: not loaded
+      const bool second = g8 + 8 < nr;
+      // rows past the chunk's count are zero in shared memory: loaded unconditionally, one pair of k-steps ahead of its MMAs
+      uint4 lo = *reinterpret_cast<const uint4*>(dr), hi = *reinterpret_cast<const uint4*>(dr + 8 * B3_DP);
 #pragma unroll
       for (int kp = 0; kp < 8; ++kp) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(dr + kp * 16);
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-        if (second) hi = *reinterpret_cast<const uint4*>(dr + 8 * B3_DP + kp * 16);
+        const uint4 lo_n = *reinterpret_cast<const uint4*>(dr + (kp < 7 ? kp + 1 : 0) * 16);
+        const uint4 hi_n = *reinterpret_cast<const uint4*>(dr + 8 * B3_DP + (kp < 7 ? kp + 1 : 0) * 16);
         const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y};
         const uint32_t a1[4] = {lo.z, hi.z, lo.w, hi.w};
 #pragma unroll
@@ -303,6 +304,8 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
           am_mma(acc[nt], a0, wb[kp][nt].x, wb[kp][nt].y);
           am_mma(acc[nt], a1, wb[kp][nt].z, wb[kp][nt].w);
         }
+        lo = lo_n;
+        hi = hi_n;
       }
       __syncwarp();
       if (lane == 0) b3_arrive_local(smem_u32(&C.rbar));  // this warp is done reading dpre of (ch, iter)
@@ -368,8 +371,10 @@ bool rec_backward_mma_applies(const RecBwdArgs& a, int* slices_out, int* nch_out
   const int slices = a.B < per_dir ? a.B : per_dir;
   const int rows = (a.B + slices - 1) / slices;
   if (rows < 8 || rows > B3_RB * B3_MAX_CHUNKS) return false;
-  int nch = (rows + B3_RB - 1) / B3_RB;
-  if (nch < 2) nch = 2;   // two chunks cover each other's head + exchange latency
+  const int nch = (rows + B3_RB - 1) / B3_RB;
+  // Rows that fit one m-tile run as ONE chunk: a second chunk would cost a second full MMA pass (the m-tile is padded to
+  // 16 rows either way), which is more than the exchange latency it hides — measured (tools/rec_bench.py, B = 128 / 240,
+  // T = 300): 2.41 / 2.55 us per step with two chunks, 1.83 / 2.05 with one (forward); 2.01 / 2.06 -> 1.54 / 1.92 (BPTT).
   *slices_out = slices;
   *nch_out = nch;
   return true;

@@ -336,8 +336,10 @@ bool rec_forward_mma_applies(const RecArgs& a, int* slices_out, int* nch_out) {
   const int slices = a.B < per_dir ? a.B : per_dir;
   const int rows = (a.B + slices - 1) / slices;
   if (rows < 8 || rows > F3_RB * F3_MAX_CHUNKS) return false;
-  int nch = (rows + F3_RB - 1) / F3_RB;
-  if (nch < 2) nch = 2;   // two chunks cover each other's tail + exchange latency
+  const int nch = (rows + F3_RB - 1) / F3_RB;
+  // Rows that fit one m-tile run as ONE chunk: a second chunk would cost a second full MMA pass (the m-tile is padded to
+  // 16 rows either way), which is more than the exchange latency it hides — measured (tools/rec_bench.py, B = 128 / 240,
+  // T = 300): 2.41 / 2.55 us per step with two chunks, 1.83 / 2.05 with one (forward); 2.01 / 2.06 -> 1.54 / 1.92 (BPTT).
   *slices_out = slices;
   *nch_out = nch;
   return true;
