@@ -162,6 +162,41 @@ def test_projection_gemm(M, N, K):
         assert rel_err(c.cpu(), ref) <= tol, flags
 
 
+@pytest.mark.parametrize("kind,M,N,K,acc", [("n", 1024, 6, 256, 0), ("n", 19200, 6, 256, 1), ("n", 70, 8, 512, 0),
+                                            ("n", 333, 3, 1024, 1), ("m", 6, 256, 19200, 1), ("m", 3, 300, 5000, 0),
+                                            ("m", 8, 1024, 4096, 0)])
+def test_skinny_gemm_of_the_output_head(kind, M, N, K, acc):
+    """The 6-wide output head (Linear(256, 6)): forward / weight gradient run on the skinny kernels (gemm_skinny_n / _m),
+    not on the 128 x 128 SIMT tile.  fp64 reference, fp32 bound; bias, accumulate, ragged sizes."""
+    from multimodalreactiongeneration_b200 import _cabi
+    L = _cabi.lib()
+    g = torch.Generator().manual_seed(6)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    ref = A.double() @ Bm.double() + bias.double() + (c0.double() if acc else 0)
+    if kind == "n":    # activation rows x weight [N][K]
+        a_dev, (a_sm, a_sk) = A.contiguous().cuda(), (K, 1)
+        b_dev, (b_sk, b_sn) = Bm.t().contiguous().cuda(), (1, K)
+    else:              # dY^T (stored [K][M]) x X (stored [K][N])
+        a_dev, (a_sm, a_sk) = A.t().contiguous().cuda(), (1, M)
+        b_dev, (b_sk, b_sn) = Bm.contiguous().cuda(), (N, 1)
+    ws = torch.empty(max(16, L.mrg_gemm_workspace_bytes(M, N, K)), dtype=torch.uint8, device="cuda")
+    c = c0.clone().cuda()
+    biasd = bias.cuda()
+    _cabi.profile_enable(True)
+    try:
+        st = L.mrg_gemm_strided(a_dev.data_ptr(), a_sm, a_sk, b_dev.data_ptr(), b_sk, b_sn, biasd.data_ptr(), c.data_ptr(),
+                                N, M, N, K, acc, 0, ws.data_ptr(), ws.numel(), 0, torch.cuda.current_stream().cuda_stream)
+        _cabi.check(st, "mrg_gemm_strided")
+        torch.cuda.synchronize()
+    finally:
+        _cabi.profile_read()
+        _cabi.profile_enable(False)
+    assert rel_err(c.cpu(), ref) <= 2e-6, (kind, M, N, K)
+
+
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K,deint", [(1024, 256, 2464, 256), (300, 256, 1024, 0), (128, 128, 32, 0),
                                          (1000, 132, 260, 0)])
