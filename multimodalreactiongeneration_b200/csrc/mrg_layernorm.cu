@@ -4,6 +4,8 @@
 // time-major LSTM output and the batch-first block input are consumed in place (no transposed copy).
 // Backward recomputes s = y + x (both are alive for the LSTM backward anyway), so the only extra state is
 // mean / rstd (8 bytes per row).  d(gamma), d(beta): per-CTA column partials + a second pass, no atomics.
+#include <cstdlib>
+
 #include "mrg_common.cuh"
 
 namespace mrg {
@@ -168,9 +170,15 @@ __global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __res
   }
 }
 
-static int ln_grid(long long rows) {
+static int ln_grid(long long rows, int per_sm) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MRG_LN_CTAS");   // tuning experiments: resident CTAs per SM (<= 4: the partial-sum workspace)
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced >= 1 && forced <= 4) per_sm = forced;
   long long blocks = (rows + 7) / 8;
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > 148 * per_sm) blocks = 148 * per_sm;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -196,7 +204,7 @@ extern "C" int mrg_residual_layernorm_forward(const float* y, long long y_s0, lo
   a.y = y; a.y_s0 = y_s0; a.y_s1 = y_s1; a.x = x; a.x_s0 = x_s0; a.x_s1 = x_s1;
   a.out = out; a.o_s0 = o_s0; a.o_s1 = o_s1; a.gamma = gamma; a.beta = beta; a.mean = mean; a.rstd = rstd;
   a.n0 = n0; a.n1 = n1; a.H = H; a.eps = eps;
-  const int grid = ln_grid(rows);
+  const int grid = ln_grid(rows, 4);   // 48 registers: 4 CTAs per SM in flight (B200, 76800 rows: 48.6 -> 37.7 us, tools/ln_bench.py)
   count_launch();
   if (H == 128) ln_fwd_kernel<1><<<grid, 256, 0, stream>>>(a);
   else if (H == 256) ln_fwd_kernel<2><<<grid, 256, 0, stream>>>(a);
@@ -227,7 +235,7 @@ extern "C" int mrg_residual_layernorm_backward(const float* dout, long long d_s0
   a.x = x; a.x_s0 = x_s0; a.x_s1 = x_s1; a.dsum = dsum; a.g_s0 = g_s0; a.g_s1 = g_s1;
   a.gamma = gamma; a.mean = const_cast<float*>(mean); a.rstd = const_cast<float*>(rstd); a.partial = (float*)workspace;
   a.n0 = n0; a.n1 = n1; a.H = H;
-  const int grid = ln_grid(rows);
+  const int grid = ln_grid(rows, 3);   // 75 registers: 3 resident CTAs per SM (71.1 -> 59.9 us; 4 is slower: a second wave)
   count_launch(2);
   if (H == 128) ln_bwd_kernel<1><<<grid, 256, 0, stream>>>(a);
   else if (H == 256) ln_bwd_kernel<2><<<grid, 256, 0, stream>>>(a);

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
   const int m1 = min(M, m0 + COLSUM_ROWS);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (n + 3 < N) {
+#pragma unroll 8
     for (int m = m0 + rp; m < m1; m += 4) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * N + n));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
