@@ -53,7 +53,10 @@ extern "C" {
 #define MRG_F_ACCUMULATE   8   /* backward: add into dw_ih / dw_hh / db instead of overwriting  */
 #define MRG_F_TF32        32   /* reduced-precision mode: the projection GEMMs run ONE tf32 tensor-core
                                   pass (10-bit mantissa, >= bf16 precision) instead of the 3-pass
-                                  fp32-grade split; the recurrence itself stays fp32               */
+                                  fp32-grade split.  H = 256 layers whose clusters get 8..48 batch rows
+                                  also run h W_hh^T / dpre W_hh as one tf32 pass on the warp-level tensor
+                                  cores (csrc/mrg_rec_fwd3.cu, mrg_rec_bwd3.cu); states, cell and
+                                  accumulation stay fp32.  Bound: 2e-2 per step / 5e-2 on gradients   */
 #define MRG_F_BF16        64   /* bf16 mode (with MRG_F_TF32): the reserve `gates` holds 4 x bfloat16 per hidden unit
                                   (8 bytes: x-projection in, gates out, d(pre-activations) back) — half the bytes of
                                   the largest buffer of the path; the GEMMs around it take / write bfloat16 and run one
