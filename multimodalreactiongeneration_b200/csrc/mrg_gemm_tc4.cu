@@ -104,13 +104,17 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   uint8_t* smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // One-pass mode with a K-major fp32 A: the raw tile IS a valid tf32 operand (the tensor core ignores the low 13 mantissa
+  // bits), so the MMAs take A straight from the TMA stage (.ss form) — no converter pass, no tensor-memory staging; the
+  // shared-memory stage is released by tcgen05.commit.  (bfloat16 or MN-major A still goes through the converters.)
+  const bool ss = p.single_pass && !p.a_bf16 && !p.a_mn;
   TC4_TRACE_DECL
   TC4_TRACE(1, 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA4; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_free(s), 4);   // the four A-converter warps have read the raw tile
+      mbar_init(a_free(s), ss ? 1 : 4);   // the four A-converter warps have read the raw tile (.ss: one tcgen05.commit)
     }
     for (int s = 0; s < ST4; ++s) {
       mbar_init(a_cvt(s), 4);    // ... have written hi | lo into tensor memory
@@ -239,7 +243,9 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         for (int i = 0; i < nkb; ++i, ++it) {
           const int sa = it % ST4, pa = (it / ST4) & 1;
           const int sb = it % SB4, pb = (it / SB4) & 1;
-          mbar_wait(a_cvt(sa), pa);
+          const int sr = it % SA4, pr = (it / SA4) & 1;   // raw A stage (.ss mode)
+          if (ss) mbar_wait(a_full(sr), pr);
+          else mbar_wait(a_cvt(sa), pa);
           mbar_wait(bh_full(sb), pb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           TC4_TRACE(20, it);
@@ -249,7 +255,10 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < TBK / 8; ++k) {
             const uint64_t dbh = make_smem_desc(b_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
-            if (lo_a) {
+            if (ss) {
+              umma_tf32(tmem_base, make_smem_desc(a_base + sr * TILE_BYTES + k * 32u, 16u, 1024u, 2u), dbh, idesc,
+                        (i > 0 || k > 0) ? 1u : 0u);
+            } else if (lo_a) {
               umma_tf32_ts(tmem_base, ta_lo + k * 8, dbh, idesc, (i > 0 || k > 0) ? 1u : 0u);
               umma_tf32_ts(tmem_base, ta_hi + k * 8, dbh, idesc, 1u);
             } else {
@@ -267,7 +276,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             }
             umma_commit(bl_empty(sb));
           }
-          umma_commit(t_empty(sa));
+          umma_commit(ss ? a_free(sr) : t_empty(sa));
           TC4_TRACE(21, it);
         }
         umma_commit(accf_bar);
@@ -296,6 +305,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int row = q * 32 + lane;  // row of the tile == TMEM lane
     uint32_t it = 0, sn = 0;
     for (int item = next_item(sn, true); item >= 0; item = next_item(sn, true)) {
+      if (ss) continue;   // nothing to convert: the role only keeps the tile ring moving
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % SA4, ph = (it / SA4) & 1;
         const int ts = it % ST4, tph = (it / ST4) & 1;

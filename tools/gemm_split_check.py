@@ -54,5 +54,9 @@ if __name__ == "__main__":
     for args in [(19200, 1024, 256, 0, True), (19200, 256, 1024, 1, False), (19200, 256, 256, 0, True),
                  (19200, 256, 256, 1, False), (19200, 512, 128, 0, True), (19200, 1024, 80, 0, True),
                  (5000, 320, 200, 0, True), (4100, 260, 36, 1, False), (76800, 1024, 256, 0, True),
-                 (19200, 1024, 256, 0, True, 32)]:
+                 (19200, 1024, 256, 0, True, 32), (19200, 256, 256, 0, True, 32), (19200, 256, 256, 1, False, 32),
+                 (76800, 1024, 256, 0, True, 32), (76800, 256, 256, 0, True, 32), (76800, 256, 256, 1, False, 32),
+                 (76800, 256, 1024, 1, False, 32)]:
+        if os.environ.get("ONLY_ONE_PASS", "0") == "1" and len(args) < 6:
+            continue
         case(*args)
