@@ -9,19 +9,24 @@
 //
 // Same ownership, exchange and chunk pipeline as rec_fwd2 (cluster of 8 CTAs, CTA c owns hidden units [32c, 32c+32),
 // st.async + mbarrier hand-off of h, cp.async prefetch of the x-projection, tail warps for the cell); what changes:
-//  * W_hh slice as tf32 B FRAGMENTS in registers: warp w of the 8 MMA warps owns the 16 gate rows of units 4w..4w+3
-//    (n index = unit * 4 + gate) over all of K = H: 32 k-steps x 2 n-tiles x 2 registers = 128 per thread — the same
-//    register footprint as the FFMA2 kernel;
-//  * a chunk holds up to 16 rows = one m-tile; A fragments (h) are read from shared memory with ONE 16-byte load per row
-//    and PAIR of k-steps: the contraction index is permuted (thread q of a quad takes memory columns 4q .. 4q+3 of a
-//    16-column group as its (k = q, q + 4) elements of two consecutive k-steps; the B fragments are loaded with the same
-//    permutation, so the sum is unchanged), row stride H + 16 floats makes those loads conflict free, rows past the
-//    chunk's row count are not loaded; h goes to the tensor core as raw fp32 bits (it ignores the low 13 mantissa bits);
+//  * the GATE rows are the M dimension of the MMA and the BATCH rows its N dimension (n-tile = 8 rows): a cluster with 17-18
+//    rows (B = 256 on 15 clusters) pays for 24 row slots, not for two 16-row m-tiles (the first version of this kernel had
+//    the batch rows on M: 1024 MMAs per CTA and step there, 768 now), and rows come in chunks of <= 8 that pipeline like the
+//    FFMA2 kernel's chunks;
+//  * W_hh slice as tf32 A FRAGMENTS in registers: warp w of the 8 MMA warps owns the m-tile of the 16 gate rows of units
+//    4w..4w+3 (m index = local unit * 4 + gate) over all of K = H: 32 k-steps x 4 registers = 128 per thread — the register
+//    footprint of the FFMA2 kernel;
+//  * B fragments (h) are read from shared memory with ONE 16-byte load per pair of k-steps: the contraction index is
+//    permuted (thread q of a quad takes memory columns 4q .. 4q+3 of a 16-column group as its (k = q, q + 4) elements of
+//    two consecutive k-steps; the A fragments are loaded with the same permutation, so the sum is unchanged), row stride
+//    H + 16 floats makes those loads conflict free; rows past the chunk's count stay zero; h goes to the tensor core as raw
+//    fp32 bits (it ignores the low 13 mantissa bits);
 //  * every MMA warp produces COMPLETE gate sums for its 16 gate rows (no k-split, no partial-sum reduction in the tail:
-//    the tail reads one float4 per (row, unit));
-//  * 8 tail warps serve rows r and r + 8 of a chunk.
+//    the tail reads one float4 per (row, unit)); the accumulator (gate row g / g + 8 x batch rows 2q, 2q + 1) is stored
+//    with a row stride of 132 floats: conflict free;
+//  * tail warp tw serves row tw of every chunk.
 // Used when the caller asks for a reduced-precision mode AND a cluster gets >= 8 rows (B >= 120 per direction): below
-// that the m-tile is mostly padding and the step is latency-bound anyway (rec_fwd2 stays).
+// that the step is latency-bound and the FFMA2 kernel is as fast (rec_fwd2 stays).
 #include <cstddef>
 #include <cstdlib>
 
@@ -30,12 +35,13 @@
 namespace mrg {
 
 constexpr int F3_THREADS = 512;   // warps 0-7: MMA role, warps 8-15: tail role
-constexpr int F3_RB = 16;         // row capacity of a chunk = one m-tile
+constexpr int F3_RB = 8;          // row capacity of a chunk = one n-tile
+constexpr int F3_PLD = 132;       // floats per row of the gate-sum buffer (128 + 4: conflict-free accumulator stores)
 
 template <int H>
 struct Fwd3Chunk {
   float h[2][F3_RB][H + 16];    // h_{t-1} of the chunk's rows, double-buffered (written by all CTAs); unused rows stay 0
-  float4 part[F3_RB][32];       // complete gate sums [row][unit] = (i, f, g, o)
+  float part[F3_RB][F3_PLD];    // complete gate sums [row][unit * 4 + gate]
   float4 xg[F3_RB][32];         // x-projection of the step being computed
   float c[F3_RB][32];           // cell state
   unsigned long long hbar[2];   // bytes of h landed in h[b]
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) rec_fwd3_kernel(RecArgs a, int 
   cluster_sync_all();  // every CTA of the cluster is running and has initialised its buffers and barriers
 
   if (warp >= 8) {
-    // =========================== tail warps: rows tw and tw + 8 of every chunk, lane = hidden unit ===================
+    // =========================== tail warps: row tw of every chunk, lane = hidden unit ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int tw = warp - 8;
     const int j = j0 + lane;
@@ -130,22 +136,19 @@ __global__ void __launch_bounds__(F3_THREADS, 1) rec_fwd3_kernel(RecArgs a, int 
       remote_base[i] = map_to_cta(smem_u32(chunks), (uint32_t)(dst < CL ? dst : 0));
     }
     const int t0 = d == 0 ? 0 : T - 1;
-    // one cp.async group per (chunk, row half) served, in the order they are consumed
+    const int r = tw;
+    // one cp.async group per chunk, in the order they are consumed
     for (int ch = 0; ch < nch; ++ch) {
       Chunk& C = chunks[ch];
       const int nr = cbase + (ch < crem ? 1 : 0);
       const int crow0 = row0 + ch * cbase + min(ch, crem);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int r = tw + 8 * half;
-        if (r < nr) {
-          C.c[r][lane] = GRU ? 0.f : c_ext[((size_t)init_slot * B + crow0 + r) * H + j];
-          if (T > 0) fetch_xg(&C.xg[r][lane], (uint32_t)t0 * BH + (uint32_t)(crow0 + r) * H + j);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+      if (r < nr) {
+        C.c[r][lane] = GRU ? 0.f : c_ext[((size_t)init_slot * B + crow0 + r) * H + j];
+        if (T > 0) fetch_xg(&C.xg[r][lane], (uint32_t)t0 * BH + (uint32_t)(crow0 + r) * H + j);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    const int ngroups = 2 * nch;   // groups committed per step by this thread
+    const int ngroups = nch;   // groups committed per step by this thread
     const int tstep = d == 0 ? 1 : -1;
     for (int step = 0; step < T; ++step) {
       const int t = d == 0 ? step : T - 1 - step;
@@ -156,64 +159,60 @@ __global__ void __launch_bounds__(F3_THREADS, 1) rec_fwd3_kernel(RecArgs a, int 
         Chunk& C = chunks[ch];
         const int nr = cbase + (ch < crem ? 1 : 0);
         const int crow0 = row0 + ch * cbase + min(ch, crem);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int r = tw + 8 * half;
-          if (r < nr) {
-            // x-projection of this step: committed `ngroups` groups ago (one step) by this thread
-            f3_wait_dyn(ngroups - 1);
-            const float4 xg = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.xg[r][lane])) : C.xg[r][lane];
-            const float cold = C.c[r][lane];
-            const uint32_t rj = (uint32_t)(crow0 + r) * H + j;
-            if (send) fetch_xg(&C.xg[r][lane], (uint32_t)(t + tstep) * BH + rj);
-            REC_TRACE(10, ch * 2 + half, step);
-            if (half == 0) mbar_wait(smem_u32(&C.pbar), cur);
-            REC_TRACE(11, ch * 2 + half, step);  // all 8 MMA warps have stored their sums (tw + 8 < nr => tw < nr)
-            const float4 p = C.part[r][lane];
-            float gi, gf, gg, go, cn, h;
-            if (GRU) {
-              gi = fast_sigmoid(p.x + xg.x);                 // r
-              gf = fast_sigmoid(p.y + xg.y);                 // z
-              go = p.w + xg.w;                               // W_hn h + b_hn
-              gg = fast_tanh(fmaf(gi, go, xg.z));            // n
-              const float hprev = C.h[cur][r][j0 + lane];
-              cn = 0.f;
-              h = fmaf(gf, hprev - gg, gg);
-            } else {
-              gi = fast_sigmoid(p.x + xg.x);
-              gf = fast_sigmoid(p.y + xg.y);
-              gg = fast_tanh(p.z + xg.z);
-              go = fast_sigmoid(p.w + xg.w);
-              cn = fmaf(gf, cold, gi * gg);
-              h = go * fast_tanh(cn);
-            }
-            if (send) {
-              float4 hv;  // h of units 4q .. 4q+3, q = lane / 4
-              hv.x = __shfl_sync(0xffffffffu, h, (lane & ~3));
-              hv.y = __shfl_sync(0xffffffffu, h, (lane & ~3) + 1);
-              hv.z = __shfl_sync(0xffffffffu, h, (lane & ~3) + 2);
-              hv.w = __shfl_sync(0xffffffffu, h, (lane & ~3) + 3);
-              const uint32_t off_h = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, h) +
-                                                ((nxt * F3_RB + r) * HP + j0 + (lane & ~3)) * sizeof(float));
-              const uint32_t off_bar = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, hbar) + nxt * 8);
-#pragma unroll
-              for (int i = 0; i < 2; ++i)
-                if ((lane & 3) + 4 * i < CL) st_async_v4(remote_base[i] + off_h, hv, remote_base[i] + off_bar);
-            }
-            REC_TRACE(12, ch * 2 + half, step);
-            y_ext[obase + rj] = h;
-            if (!GRU) {
-              C.c[r][lane] = cn;
-              c_ext[obase + rj] = cn;
-            }
-            if (a.train) {
-              const size_t gidx = (size_t)((uint32_t)t * BH + rj);
-              if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(gi, gf, gg, go);
-              else reinterpret_cast<float4*>(gates_b)[gidx] = make_float4(gi, gf, gg, go);
-            }
+        if (r < nr) {
+          // x-projection of this step: committed `ngroups` groups ago (one step) by this thread
+          f3_wait_dyn(ngroups - 1);
+          const float4 xg = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.xg[r][lane])) : C.xg[r][lane];
+          const float cold = C.c[r][lane];
+          const uint32_t rj = (uint32_t)(crow0 + r) * H + j;
+          if (send) fetch_xg(&C.xg[r][lane], (uint32_t)(t + tstep) * BH + rj);
+          REC_TRACE(10, ch, step);
+          mbar_wait(smem_u32(&C.pbar), cur);
+          REC_TRACE(11, ch, step);  // all 8 MMA warps have stored their sums
+          const float4 p = *reinterpret_cast<const float4*>(&C.part[r][lane * 4]);
+          float gi, gf, gg, go, cn, h;
+          if (GRU) {
+            gi = fast_sigmoid(p.x + xg.x);                 // r
+            gf = fast_sigmoid(p.y + xg.y);                 // z
+            go = p.w + xg.w;                               // W_hn h + b_hn
+            gg = fast_tanh(fmaf(gi, go, xg.z));            // n
+            const float hprev = C.h[cur][r][j0 + lane];
+            cn = 0.f;
+            h = fmaf(gf, hprev - gg, gg);
+          } else {
+            gi = fast_sigmoid(p.x + xg.x);
+            gf = fast_sigmoid(p.y + xg.y);
+            gg = fast_tanh(p.z + xg.z);
+            go = fast_sigmoid(p.w + xg.w);
+            cn = fmaf(gf, cold, gi * gg);
+            h = go * fast_tanh(cn);
           }
-          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (send) {
+            float4 hv;  // h of units 4q .. 4q+3, q = lane / 4
+            hv.x = __shfl_sync(0xffffffffu, h, (lane & ~3));
+            hv.y = __shfl_sync(0xffffffffu, h, (lane & ~3) + 1);
+            hv.z = __shfl_sync(0xffffffffu, h, (lane & ~3) + 2);
+            hv.w = __shfl_sync(0xffffffffu, h, (lane & ~3) + 3);
+            const uint32_t off_h = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, h) +
+                                              ((nxt * F3_RB + r) * HP + j0 + (lane & ~3)) * sizeof(float));
+            const uint32_t off_bar = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, hbar) + nxt * 8);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if ((lane & 3) + 4 * i < CL) st_async_v4(remote_base[i] + off_h, hv, remote_base[i] + off_bar);
+          }
+          REC_TRACE(12, ch, step);
+          y_ext[obase + rj] = h;
+          if (!GRU) {
+            C.c[r][lane] = cn;
+            c_ext[obase + rj] = cn;
+          }
+          if (a.train) {
+            const size_t gidx = (size_t)((uint32_t)t * BH + rj);
+            if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(gi, gf, gg, go);
+            else reinterpret_cast<float4*>(gates_b)[gidx] = make_float4(gi, gf, gg, go);
+          }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -224,18 +223,21 @@ __global__ void __launch_bounds__(F3_THREADS, 1) rec_fwd3_kernel(RecArgs a, int 
   asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
   const int g8 = lane >> 2, q = lane & 3;
   const float* __restrict__ W = d == 0 ? a.w_hh[0] : a.w_hh[1];
-  // B fragments of W_hh^T for this warp's 16 gate rows, n = unit * 4 + gate: n-tile nt, column g8 -> local unit
-  // 4 warp + 2 nt + (g8 >> 2), gate g8 & 3.  Per pair of k-steps kp the thread holds memory columns 16 kp + 4q .. + 3:
-  // (b0, b1) of the even k-step, (b0, b1) of the odd one.  tf32 rounding once, here.
-  uint4 wb[KP][2];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int unit = warp * 4 + nt * 2 + (g8 >> 2), gate = g8 & 3;
-    const float* wrow = W + (size_t)(gate * H + j0 + unit) * H;
+  // A fragments of this warp's m-tile: m = local unit * 4 + gate, fragment rows g8 / g8 + 8 -> units 4 warp + (g8 >> 2) and
+  // 4 warp + 2 + (g8 >> 2), gate g8 & 3.  Per pair of k-steps kp the thread holds memory columns 16 kp + 4q .. + 3 of both
+  // rows: (a0, a1, a2, a3) of the even k-step = (row g8 col 0, row g8+8 col 0, row g8 col 1, row g8+8 col 1), of the odd
+  // k-step the same with columns 2, 3.  tf32 rounding once, here.
+  uint4 wa[KP][2];
+  {
+    const int gate = g8 & 3;
+    const float* wr0 = W + (size_t)(gate * H + j0 + warp * 4 + (g8 >> 2)) * H;
+    const float* wr1 = wr0 + (size_t)2 * H;
 #pragma unroll
     for (int kp = 0; kp < KP; ++kp) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + kp * 16 + 4 * q));
-      wb[kp][nt] = make_uint4(tf32_rna(w4.x), tf32_rna(w4.y), tf32_rna(w4.z), tf32_rna(w4.w));
+      const float4 lo = __ldg(reinterpret_cast<const float4*>(wr0 + kp * 16 + 4 * q));
+      const float4 hi = __ldg(reinterpret_cast<const float4*>(wr1 + kp * 16 + 4 * q));
+      wa[kp][0] = make_uint4(tf32_rna(lo.x), tf32_rna(hi.x), tf32_rna(lo.y), tf32_rna(hi.y));
+      wa[kp][1] = make_uint4(tf32_rna(lo.z), tf32_rna(hi.z), tf32_rna(lo.w), tf32_rna(hi.w));
     }
   }
   uint32_t hphases = 0;  // bit (ch*2 + buf): parity of hbar to wait for next
@@ -255,32 +257,29 @@ __global__ void __launch_bounds__(F3_THREADS, 1) rec_fwd3_kernel(RecArgs a, int 
       REC_TRACE(2, ch, step);
       // re-arm this buffer's barrier for the round of step+1 (which writes C.h[cur] again)
       if (tid == 0 && step + 2 < T) mbar_arrive_expect_tx(hbar_cur, (uint32_t)(nr * H * sizeof(float)));
-      float acc[2][4];
+      float acc[4][4];   // four independent accumulator chains (k-step mod 4), summed at the end
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      const float* hr = &C.h[cur][g8][4 * q];
-      const bool second = g8 + 8 < nr;   // rows past the chunk's count are zero: not loaded
+      for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+      const float* hr = &C.h[cur][g8][4 * q];   // B fragment: batch row g8 (rows past the chunk's count are zero)
 #pragma unroll
       for (int kp = 0; kp < KP; ++kp) {
-        // A fragments of two k-steps: rows g8 / g8 + 8, memory columns 16 kp + 4q .. + 3 (see wb)
-        const uint4 lo = *reinterpret_cast<const uint4*>(hr + kp * 16);
-        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-        if (second) hi = *reinterpret_cast<const uint4*>(hr + 8 * HP + kp * 16);
-        const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y};
-        const uint32_t a1[4] = {lo.z, hi.z, lo.w, hi.w};
-        am_mma(acc[0], a0, wb[kp][0].x, wb[kp][0].y);
-        am_mma(acc[1], a0, wb[kp][1].x, wb[kp][1].y);
-        am_mma(acc[0], a1, wb[kp][0].z, wb[kp][0].w);
-        am_mma(acc[1], a1, wb[kp][1].z, wb[kp][1].w);
+        const uint4 v = *reinterpret_cast<const uint4*>(hr + kp * 16);
+        const uint32_t a0[4] = {wa[kp][0].x, wa[kp][0].y, wa[kp][0].z, wa[kp][0].w};
+        const uint32_t a1[4] = {wa[kp][1].x, wa[kp][1].y, wa[kp][1].z, wa[kp][1].w};
+        am_mma(acc[(2 * kp) & 3], a0, v.x, v.y);
+        am_mma(acc[(2 * kp + 1) & 3], a1, v.z, v.w);
       }
-      // accumulator: rows g8 / g8 + 8, n-tile columns 2q, 2q + 1 -> unit 4 warp + 2 nt + (q >> 1), gates 2 (q & 1) + {0, 1}
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int unit = warp * 4 + nt * 2 + (q >> 1);
-        float* p0 = reinterpret_cast<float*>(&C.part[g8][unit]) + 2 * (q & 1);
-        float* p1 = reinterpret_cast<float*>(&C.part[g8 + 8][unit]) + 2 * (q & 1);
-        if (g8 < nr) *reinterpret_cast<float2*>(p0) = make_float2(acc[nt][0], acc[nt][1]);
-        if (g8 + 8 < nr) *reinterpret_cast<float2*>(p1) = make_float2(acc[nt][2], acc[nt][3]);
+      // accumulator: gate rows m = g8 / g8 + 8 of this warp's m-tile x batch rows 2q, 2q + 1 -> part[row][16 warp + m]
+      {
+        const float s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+        const float s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+        const float s2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+        const float s3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+        float* pr = &C.part[2 * q][16 * warp + g8];
+        pr[0] = s0;
+        pr[F3_PLD] = s1;
+        pr[8] = s2;
+        pr[F3_PLD + 8] = s3;
       }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&C.pbar)) : "memory");
@@ -290,7 +289,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) rec_fwd3_kernel(RecArgs a, int 
   // Exit safety as in rec_fwd2: the last round of remote stores into this CTA (step T-2) was waited for at step T-1.
 }
 
-constexpr int F3_MAX_CHUNKS = 4;
+constexpr int F3_MAX_CHUNKS = 8;
 
 template <int H, bool GRU>
 static int launch_fwd3(const RecArgs& a, int slices, int nch, cudaStream_t stream) {
@@ -320,7 +319,7 @@ static int launch_fwd3(const RecArgs& a, int slices, int nch, cudaStream_t strea
   return 0;
 }
 
-// Does the tensor-core forward apply?  Reduced-precision call, H = 256, one wave of clusters with 8 .. 64 rows each.
+// Does the tensor-core forward apply?  Reduced-precision call, H = 256, one wave of clusters with 8 .. 64 rows each (chunks of <= 8 rows).
 bool rec_forward_mma_applies(const RecArgs& a, int* slices_out, int* nch_out) {
   static int off = -1;
   if (off < 0) {
@@ -337,9 +336,7 @@ bool rec_forward_mma_applies(const RecArgs& a, int* slices_out, int* nch_out) {
   const int rows = (a.B + slices - 1) / slices;
   if (rows < 8 || rows > F3_RB * F3_MAX_CHUNKS) return false;
   const int nch = (rows + F3_RB - 1) / F3_RB;
-  // Rows that fit one m-tile run as ONE chunk: a second chunk would cost a second full MMA pass (the m-tile is padded to
-  // 16 rows either way), which is more than the exchange latency it hides — measured (tools/rec_bench.py, B = 128 / 240,
-  // T = 300): 2.41 / 2.55 us per step with two chunks, 1.83 / 2.05 with one (forward); 2.01 / 2.06 -> 1.54 / 1.92 (BPTT).
+  // chunks of <= 8 rows (one n-tile each): the MMA work is proportional to the number of chunks, so as few as the rows need
   *slices_out = slices;
   *nch_out = nch;
   return true;
