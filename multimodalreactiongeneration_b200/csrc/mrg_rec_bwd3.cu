@@ -9,17 +9,18 @@
 // Same ownership and exchange as rec_bwd2 (cluster of 8 CTAs, CTA c owns hidden units [32c, 32c+32) and their 128 gate
 // rows of W_hh; every CTA produces a partial dh over ALL 256 columns from its 128 gate rows, the owner of a column sums
 // the 8 partials in fixed order; head warps / body warps meet through mbarriers only).  What changes:
-//  * W_hh slice as tf32 B FRAGMENTS in registers: the contraction runs over the CTA's 128 gate rows (16 k-steps), body
-//    warp w owns output columns [32w, 32w+32) = four n-tiles: 16 x 4 x 2 = 128 registers per thread, the footprint of
+//  * the OUTPUT columns are the M dimension of the MMA and the BATCH rows its N dimension (n-tile = 8 rows = one chunk), as
+//    in rec_fwd3: 17-18 rows per cluster pay for 24 row slots instead of two 16-row m-tiles, and the chunks pipeline;
+//  * W_hh slice as tf32 A FRAGMENTS in registers: the contraction runs over the CTA's 128 gate rows (16 k-steps), body
+//    warp w owns output columns [32w, 32w+32) = two m-tiles: 16 x 2 x 4 = 128 registers per thread, the footprint of
 //    the FFMA2 kernel.  Every output column of warp w belongs to CTA w: one destination per warp;
-//  * a chunk holds up to 16 rows = one m-tile; A fragments (dpre) are read with ONE 16-byte load per row and pair of
-//    k-steps — thread q of a quad takes the four gates of unit 4 kp + q as its (k = q, q + 4) elements of two
-//    consecutive k-steps, B loaded with the same permutation; row stride 128 + 16 floats: conflict free.  dpre goes to
-//    the tensor core as raw fp32 bits;
-//  * the n-tile columns are permuted so that a thread's accumulators of a tile PAIR are four consecutive columns: one
-//    16-byte st.async per (row, tile pair) straight from the accumulators, no shuffle reduce;
-//  * 8 head warps serve rows r and r + 8 of every chunk.
-// Used when the caller asks for a reduced-precision mode AND a cluster gets 8 .. 48 rows (three chunks of shared memory).
+//  * B fragments (dpre) are read with ONE 16-byte load per pair of k-steps — thread q of a quad takes the four gates of
+//    unit 4 kp + q as its (k = q, q + 4) elements of two consecutive k-steps, A loaded with the same permutation; row
+//    stride 128 + 16 floats: conflict free.  dpre goes to the tensor core as raw fp32 bits;
+//  * the m-tile rows are permuted so that a thread's four accumulator rows (two m-tiles x rows g, g + 8) are four
+//    CONSECUTIVE output columns: one 16-byte st.async per batch row straight from the accumulators, no shuffle reduce;
+//  * head warp hw serves row hw of every chunk.
+// Used when the caller asks for a reduced-precision mode AND a cluster gets 8 .. 48 rows (six chunks of shared memory).
 #include <cstddef>
 #include <cstdlib>
 
@@ -28,9 +29,9 @@
 namespace mrg {
 
 constexpr int B3_THREADS = 512;   // warps 0-7: body (MMA) role, warps 8-15: head role
-constexpr int B3_RB = 16;         // row capacity of a chunk = one m-tile
+constexpr int B3_RB = 8;          // row capacity of a chunk = one n-tile
 constexpr int B3_DP = 128 + 16;   // row stride of dpre in floats
-constexpr int B3_MAX_CHUNKS = 3;
+constexpr int B3_MAX_CHUNKS = 6;
 
 template <int H>
 struct Bwd3Chunk {
@@ -121,12 +122,13 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
   __syncthreads();
 
   if (warp >= 8) {
-    // =========================== head warps: rows hw and hw + 8 of every chunk, lane = hidden unit =================
+    // =========================== head warps: row hw of every chunk, lane = hidden unit ==============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int hw = warp - 8;
+    const int r = hw;
     const int j = j0 + lane;
-    const int ngroups = 2 * nch;  // cp.async groups committed per step by this thread
-    auto prefetch = [&](Chunk& C, int crow0, int r, int step) {
+    const int ngroups = nch;  // cp.async groups committed per step by this thread
+    auto prefetch = [&](Chunk& C, int crow0, int step) {
       const int t = d == 0 ? step : T - 1 - step;
       const int prev_slot = d == 0 ? t : t + 1;
       const uint32_t rj = (uint32_t)(crow0 + r) * H + j;
@@ -139,25 +141,21 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
       Chunk& C = chunks[ch];
       const int nr = cbase + (ch < crem ? 1 : 0);
       const int crow0 = row0 + ch * cbase + min(ch, crem);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int r = hw + 8 * half;
-        if (r < nr) {
-          const size_t row = crow0 + r;
-          C.db[r][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-          C.dy[r][lane] = 0.f;
-          C.dc[r][lane] = (!GRU && a.dc_n) ? a.dc_n[((size_t)d * B + row) * H + j] : 0.f;
-          if (T > 0) {
-            const int t_last = d == 0 ? T - 1 : 0;
-            const int out_slot = d == 0 ? t_last + 1 : t_last;
-            C.c_cur[r][lane] = GRU ? 0.f : c_ext[((size_t)out_slot * B + row) * H + j];
-            prefetch(C, crow0, r, T - 1);
-          }
-          // the first iteration reads dh_n through source slot 0 of part[0]
-          if (a.dh_n) C.part[0][0][r][lane] = a.dh_n[((size_t)d * B + row) * H + j];
+      if (r < nr) {
+        const size_t row = crow0 + r;
+        C.db[r][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        C.dy[r][lane] = 0.f;
+        C.dc[r][lane] = (!GRU && a.dc_n) ? a.dc_n[((size_t)d * B + row) * H + j] : 0.f;
+        if (T > 0) {
+          const int t_last = d == 0 ? T - 1 : 0;
+          const int out_slot = d == 0 ? t_last + 1 : t_last;
+          C.c_cur[r][lane] = GRU ? 0.f : c_ext[((size_t)out_slot * B + row) * H + j];
+          prefetch(C, crow0, T - 1);
         }
-        b3_commit();
+        // the first iteration reads dh_n through source slot 0 of part[0]
+        if (a.dh_n) C.part[0][0][r][lane] = a.dh_n[((size_t)d * B + row) * H + j];
       }
+      b3_commit();
     }
     cluster_sync_all();
     uint32_t hphases = 0;  // bit (ch*2 + buf) = parity of hbar to wait for next
@@ -170,63 +168,57 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
         const int nr = cbase + (ch < crem ? 1 : 0);
         const int crow0 = row0 + ch * cbase + min(ch, crem);
         const uint32_t hbar_cur = smem_u32(&C.hbar[cur]);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int r = hw + 8 * half;
-          if (r < nr) {
-            // loads of this step: committed `ngroups` groups ago (one step) by this thread
-            b3_wait_dyn(ngroups - 1);
-            const float4 g = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.g[r][lane])) : C.g[r][lane];
-            const float cprev = C.cp[r][lane];
-            float dh = C.dy[r][lane];
-            const float tc = GRU ? 0.f : fast_tanh(C.c_cur[r][lane]);
-            const float dcin = C.dc[r][lane];
-            if (iter + 1 < T) prefetch(C, crow0, r, step - 1);
-            if (half == 0) {  // hw + 8 < nr implies hw < nr: the second row runs behind the first row's waits
-              if (iter > 0) {  // the partial dh of all source CTAs have landed in part[cur]
-                mbar_wait(hbar_cur, (hphases >> (ch * 2 + cur)) & 1u);
-                hphases ^= 1u << (ch * 2 + cur);
-              }
-              // re-arm for the round of iteration iter+1 (which writes part[cur] again)
-              if (hw == 0 && lane == 0 && iter + 1 < T)
-                mbar_arrive_expect_tx(hbar_cur, (uint32_t)(CL * nr * 32 * sizeof(float)));
-              // dpre may only be overwritten once all 8 local body warps have read the previous step
-              if (iter > 0) mbar_wait(smem_u32(&C.rbar), (uint32_t)((iter - 1) & 1));
-            }
-#pragma unroll
-            for (int s = 0; s < CL; ++s) dh += C.part[cur][s][r][lane];
-            float4 dp;
-            float carry;
-            if (GRU) {
-              dh += dcin;                                            // direct path dh_{t+1} z_{t+1}
-              const float dnp = dh * (1.f - g.y) * (1.f - g.z * g.z);
-              const float dzp = dh * (cprev - g.z) * g.y * (1.f - g.y);   // cprev = h_{t-1}
-              dp = make_float4(dnp * g.w * g.x * (1.f - g.x), dzp, dnp, dnp * g.x);
-              carry = dh * g.y;
-            } else {
-              const float d_o = dh * tc;
-              const float dct = dcin + dh * g.w * (1.f - tc * tc);
-              const float d_i = dct * g.z, d_g = dct * g.x, d_f = dct * cprev;
-              dp = make_float4(d_i * g.x * (1.f - g.x), d_f * g.y * (1.f - g.y), d_g * (1.f - g.z * g.z),
-                               d_o * g.w * (1.f - g.w));
-              carry = dct * g.y;
-            }
-            *reinterpret_cast<float4*>(&C.dpre[r][lane * 4]) = dp;
-            __syncwarp();
-            if (lane == 0) b3_arrive_local(smem_u32(&C.dbar));
-            C.dc[r][lane] = carry;
-            if (!GRU) C.c_cur[r][lane] = cprev;
-            float4 db = C.db[r][lane];
-            db.x += dp.x; db.y += dp.y; db.z += dp.z; db.w += dp.w;
-            C.db[r][lane] = db;
-            {
-              const size_t gidx = (size_t)((uint32_t)t * BH + (uint32_t)(crow0 + r) * H + j);
-              if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(dp.x, dp.y, dp.z, dp.w);
-              else reinterpret_cast<float4*>(gates_b)[gidx] = dp;
-            }
+        if (r < nr) {
+          // loads of this step: committed `ngroups` groups ago (one step) by this thread
+          b3_wait_dyn(ngroups - 1);
+          const float4 g = bf ? unpack_bf16x4(*reinterpret_cast<const uint2*>(&C.g[r][lane])) : C.g[r][lane];
+          const float cprev = C.cp[r][lane];
+          float dh = C.dy[r][lane];
+          const float tc = GRU ? 0.f : fast_tanh(C.c_cur[r][lane]);
+          const float dcin = C.dc[r][lane];
+          if (iter + 1 < T) prefetch(C, crow0, step - 1);
+          if (iter > 0) {  // the partial dh of all source CTAs have landed in part[cur]
+            mbar_wait(hbar_cur, (hphases >> (ch * 2 + cur)) & 1u);
+            hphases ^= 1u << (ch * 2 + cur);
           }
-          b3_commit();
+          // re-arm for the round of iteration iter+1 (which writes part[cur] again)
+          if (hw == 0 && lane == 0 && iter + 1 < T)
+            mbar_arrive_expect_tx(hbar_cur, (uint32_t)(CL * nr * 32 * sizeof(float)));
+          // dpre may only be overwritten once all 8 local body warps have read the previous step
+          if (iter > 0) mbar_wait(smem_u32(&C.rbar), (uint32_t)((iter - 1) & 1));
+#pragma unroll
+          for (int s = 0; s < CL; ++s) dh += C.part[cur][s][r][lane];
+          float4 dp;
+          float carry;
+          if (GRU) {
+            dh += dcin;                                            // direct path dh_{t+1} z_{t+1}
+            const float dnp = dh * (1.f - g.y) * (1.f - g.z * g.z);
+            const float dzp = dh * (cprev - g.z) * g.y * (1.f - g.y);   // cprev = h_{t-1}
+            dp = make_float4(dnp * g.w * g.x * (1.f - g.x), dzp, dnp, dnp * g.x);
+            carry = dh * g.y;
+          } else {
+            const float d_o = dh * tc;
+            const float dct = dcin + dh * g.w * (1.f - tc * tc);
+            const float d_i = dct * g.z, d_g = dct * g.x, d_f = dct * cprev;
+            dp = make_float4(d_i * g.x * (1.f - g.x), d_f * g.y * (1.f - g.y), d_g * (1.f - g.z * g.z),
+                             d_o * g.w * (1.f - g.w));
+            carry = dct * g.y;
+          }
+          *reinterpret_cast<float4*>(&C.dpre[r][lane * 4]) = dp;
+          __syncwarp();
+          if (lane == 0) b3_arrive_local(smem_u32(&C.dbar));
+          C.dc[r][lane] = carry;
+          if (!GRU) C.c_cur[r][lane] = cprev;
+          float4 db = C.db[r][lane];
+          db.x += dp.x; db.y += dp.y; db.z += dp.z; db.w += dp.w;
+          C.db[r][lane] = db;
+          {
+            const size_t gidx = (size_t)((uint32_t)t * BH + (uint32_t)(crow0 + r) * H + j);
+            if (bf) reinterpret_cast<uint2*>(gates_b)[gidx] = pack_bf16x4(dp.x, dp.y, dp.z, dp.w);
+            else reinterpret_cast<float4*>(gates_b)[gidx] = dp;
+          }
         }
+        b3_commit();
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -236,21 +228,17 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
       Chunk& C = chunks[ch];
       const int nr = cbase + (ch < crem ? 1 : 0);
       const int crow0 = row0 + ch * cbase + min(ch, crem);
-      if (hw < nr && T > 0) mbar_wait(smem_u32(&C.hbar[fin]), (hphases >> (ch * 2 + fin)) & 1u);
+      if (r >= nr) continue;
+      if (T > 0) mbar_wait(smem_u32(&C.hbar[fin]), (hphases >> (ch * 2 + fin)) & 1u);
+      const size_t row = crow0 + r;
+      float dh = 0.f;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int r = hw + 8 * half;
-        if (r >= nr) continue;
-        const size_t row = crow0 + r;
-        float dh = 0.f;
-#pragma unroll
-        for (int s = 0; s < CL; ++s) dh += C.part[fin][s][r][lane];
-        float* dh0 = d == 0 ? a.dh0[0] : a.dh0[1];
-        float* dc0 = d == 0 ? a.dc0[0] : a.dc0[1];
-        if (dh0) dh0[row * H + j] = GRU ? dh + C.dc[r][lane] : dh;
-        if (dc0 && !GRU) dc0[row * H + j] = C.dc[r][lane];
-        *reinterpret_cast<float4*>(a.db_part + (((size_t)d * B + row) * H + j) * 4) = C.db[r][lane];
-      }
+      for (int s = 0; s < CL; ++s) dh += C.part[fin][s][r][lane];
+      float* dh0 = d == 0 ? a.dh0[0] : a.dh0[1];
+      float* dc0 = d == 0 ? a.dc0[0] : a.dc0[1];
+      if (dh0) dh0[row * H + j] = GRU ? dh + C.dc[r][lane] : dh;
+      if (dc0 && !GRU) dc0[row * H + j] = C.dc[r][lane];
+      *reinterpret_cast<float4*>(a.db_part + (((size_t)d * B + row) * H + j) * 4) = C.db[r][lane];
     }
     return;
   }
@@ -259,20 +247,22 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
   asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
   const int g8 = lane >> 2, q = lane & 3;
   const float* __restrict__ W = d == 0 ? a.w_hh[0] : a.w_hh[1];
-  // B fragments of this CTA's W_hh rows for output columns [32 warp, 32 warp + 32).  n-tile nt = 2 p + s, fragment column
-  // c -> memory column 32 warp + 16 p + 4 (c >> 1) + 2 s + (c & 1): the accumulator columns (2q, 2q + 1) of tiles 2p and
-  // 2p + 1 are the four consecutive columns 32 warp + 16 p + 4 q .. + 3.  Contraction: per pair of k-steps kp the thread
-  // holds the four gate rows of local unit 4 kp + q — (gate 0, gate 1) = (b0, b1) of the even k-step, (gate 2, gate 3) of the
-  // odd one — matching the A load below.  tf32 rounding once, here.
-  uint4 wb[8][4];
+  // A fragments (W_hh^T) of this warp's two m-tiles.  Output column of m-tile t, fragment row g8 (+ 8): 32 warp + 4 g8 + 2 t
+  // (+ 1) — the thread's four accumulator rows are the consecutive columns 32 warp + 4 g8 .. + 3.  Contraction: per pair of
+  // k-steps kp the thread holds the four gate rows of local unit 4 kp + q — (gate 0, gate 1) = the (k = q, q + 4) elements of
+  // the even k-step, (gate 2, gate 3) of the odd one — matching the B load below.  (a0, a1, a2, a3) = (row g8 k = q,
+  // row g8 + 8 k = q, row g8 k = q + 4, row g8 + 8 k = q + 4).  tf32 rounding once, here.
+  uint4 wa[8][2][2];   // [kp][even / odd k-step][m-tile]
 #pragma unroll
   for (int kp = 0; kp < 8; ++kp) {
-    const float* wrow = W + (size_t)(j0 + 4 * kp + q) * H + 32 * warp;
+    const float* wrow = W + (size_t)(j0 + 4 * kp + q) * H + 32 * warp + 4 * g8;
+    float4 gw[4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = 16 * (nt >> 1) + 4 * (g8 >> 1) + 2 * (nt & 1) + (g8 & 1);
-      wb[kp][nt] = make_uint4(tf32_rna(__ldg(wrow + col)), tf32_rna(__ldg(wrow + (size_t)H * H + col)),
-                              tf32_rna(__ldg(wrow + (size_t)2 * H * H + col)), tf32_rna(__ldg(wrow + (size_t)3 * H * H + col)));
+    for (int gate = 0; gate < 4; ++gate) gw[gate] = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)gate * H * H));
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      wa[kp][e][0] = make_uint4(tf32_rna(gw[2 * e].x), tf32_rna(gw[2 * e].y), tf32_rna(gw[2 * e + 1].x), tf32_rna(gw[2 * e + 1].y));
+      wa[kp][e][1] = make_uint4(tf32_rna(gw[2 * e].z), tf32_rna(gw[2 * e].w), tf32_rna(gw[2 * e + 1].z), tf32_rna(gw[2 * e + 1].w));
     }
   }
   // every output column of this warp belongs to CTA `warp`
@@ -286,42 +276,42 @@ __global__ void __launch_bounds__(B3_THREADS, 1) rec_bwd3_kernel(RecBwdArgs a, i
       const int nr = cbase + (ch < crem ? 1 : 0);
       if (nr == 0) continue;
       mbar_wait(smem_u32(&C.dbar), (uint32_t)(iter & 1));  // dpre of (ch, iter) is published
-      float acc[4][4];
+      float acc[2][2][4];   // [m-tile][even / odd k-step]: four independent chains
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      const float* dr = &C.dpre[g8][4 * q];
-      const bool second = g8 + 8 < nr;
-      // rows past the chunk's count are zero in shared memory: loaded unconditionally, one pair of k-steps ahead of its MMAs
-      uint4 lo = *reinterpret_cast<const uint4*>(dr), hi = *reinterpret_cast<const uint4*>(dr + 8 * B3_DP);
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[t][e][0] = acc[t][e][1] = acc[t][e][2] = acc[t][e][3] = 0.f;
+      const float* dr = &C.dpre[g8][4 * q];   // B fragment: batch row g8 (rows past the chunk's count stay zero)
+      uint4 v = *reinterpret_cast<const uint4*>(dr);
 #pragma unroll
       for (int kp = 0; kp < 8; ++kp) {
-        const uint4 lo_n = *reinterpret_cast<const uint4*>(dr + (kp < 7 ? kp + 1 : 0) * 16);
-        const uint4 hi_n = *reinterpret_cast<const uint4*>(dr + 8 * B3_DP + (kp < 7 ? kp + 1 : 0) * 16);
-        const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y};
-        const uint32_t a1[4] = {lo.z, hi.z, lo.w, hi.w};
+        const uint4 vn = *reinterpret_cast<const uint4*>(dr + (kp < 7 ? kp + 1 : 0) * 16);   // one pair of k-steps ahead
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          am_mma(acc[nt], a0, wb[kp][nt].x, wb[kp][nt].y);
-          am_mma(acc[nt], a1, wb[kp][nt].z, wb[kp][nt].w);
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t a0[4] = {wa[kp][0][t].x, wa[kp][0][t].y, wa[kp][0][t].z, wa[kp][0][t].w};
+          const uint32_t a1[4] = {wa[kp][1][t].x, wa[kp][1][t].y, wa[kp][1][t].z, wa[kp][1][t].w};
+          am_mma(acc[t][0], a0, v.x, v.y);
+          am_mma(acc[t][1], a1, v.z, v.w);
         }
-        lo = lo_n;
-        hi = hi_n;
+        v = vn;
       }
       __syncwarp();
       if (lane == 0) b3_arrive_local(smem_u32(&C.rbar));  // this warp is done reading dpre of (ch, iter)
-      // ---- one 16-byte store per (row, tile pair) to the owner of this warp's columns ----------------------------
+      // ---- one 16-byte store per batch row to the owner of this warp's columns ------------------------------------
+      // accumulator element e of m-tile t: (row g8 | g8 + 8) x (batch row 2q | 2q + 1) -> column 4 g8 + 2 t + (e >> 1)
       const uint32_t off_bar = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, hbar) + nxt * 8);
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const uint32_t off = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, part) +
-                                        (((nxt * CL + (int)rank) * B3_RB + g8) * 32 + 16 * p + 4 * q) * sizeof(float));
-        if (g8 < nr)
-          st_async_v4(remote_base + off, make_float4(acc[2 * p][0], acc[2 * p][1], acc[2 * p + 1][0], acc[2 * p + 1][1]),
-                      remote_base + off_bar);
-        if (second)
-          st_async_v4(remote_base + off + 8 * 32 * sizeof(float),
-                      make_float4(acc[2 * p][2], acc[2 * p][3], acc[2 * p + 1][2], acc[2 * p + 1][3]), remote_base + off_bar);
-      }
+      const uint32_t off = (uint32_t)(ch * sizeof(Chunk) + offsetof(Chunk, part) +
+                                      (((nxt * CL + (int)rank) * B3_RB + 2 * q) * 32 + 4 * g8) * sizeof(float));
+      if (2 * q < nr)
+        st_async_v4(remote_base + off,
+                    make_float4(acc[0][0][0] + acc[0][1][0], acc[0][0][2] + acc[0][1][2], acc[1][0][0] + acc[1][1][0],
+                                acc[1][0][2] + acc[1][1][2]),
+                    remote_base + off_bar);
+      if (2 * q + 1 < nr)
+        st_async_v4(remote_base + off + 32 * sizeof(float),
+                    make_float4(acc[0][0][1] + acc[0][1][1], acc[0][0][3] + acc[0][1][3], acc[1][0][1] + acc[1][1][1],
+                                acc[1][0][3] + acc[1][1][3]),
+                    remote_base + off_bar);
     }
   }
 }
@@ -372,9 +362,7 @@ bool rec_backward_mma_applies(const RecBwdArgs& a, int* slices_out, int* nch_out
   const int rows = (a.B + slices - 1) / slices;
   if (rows < 8 || rows > B3_RB * B3_MAX_CHUNKS) return false;
   const int nch = (rows + B3_RB - 1) / B3_RB;
-  // Rows that fit one m-tile run as ONE chunk: a second chunk would cost a second full MMA pass (the m-tile is padded to
-  // 16 rows either way), which is more than the exchange latency it hides — measured (tools/rec_bench.py, B = 128 / 240,
-  // T = 300): 2.41 / 2.55 us per step with two chunks, 1.83 / 2.05 with one (forward); 2.01 / 2.06 -> 1.54 / 1.92 (BPTT).
+  // chunks of <= 8 rows (one n-tile each): the MMA work is proportional to the number of chunks, so as few as the rows need
   *slices_out = slices;
   *nch_out = nch;
   return true;
