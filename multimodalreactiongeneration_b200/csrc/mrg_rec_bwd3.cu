@@ -20,7 +20,8 @@
 //  * the m-tile rows are permuted so that a thread's four accumulator rows (two m-tiles x rows g, g + 8) are four
 //    CONSECUTIVE output columns: one 16-byte st.async per batch row straight from the accumulators, no shuffle reduce;
 //  * head warp hw serves row hw of every chunk.
-// Used when the caller asks for a reduced-precision mode AND a cluster gets 8 .. 48 rows (six chunks of shared memory).
+// Used whenever the caller asks for a reduced-precision mode at H = 256 and a cluster gets <= 48 rows (six chunks of shared
+// memory); measurements in mrg_rec_fwd3.cu.
 #include <cstddef>
 #include <cstdlib>
 
@@ -344,7 +345,7 @@ static int launch_bwd3(const RecBwdArgs& a, int slices, int nch, cudaStream_t st
   return 0;
 }
 
-// Does the tensor-core BPTT apply?  Reduced-precision call, H = 256, one wave of clusters with 8 .. 48 rows each.  The row
+// Does the tensor-core BPTT apply?  Reduced-precision call, H = 256, one wave of clusters with <= 48 rows each.  The row
 // partition is this kernel's own (the reserve is indexed by row: it need not match the forward's).
 bool rec_backward_mma_applies(const RecBwdArgs& a, int* slices_out, int* nch_out) {
   static int off = -1;
@@ -360,7 +361,7 @@ bool rec_backward_mma_applies(const RecBwdArgs& a, int* slices_out, int* nch_out
   if (per_dir < 1) per_dir = 1;
   const int slices = a.B < per_dir ? a.B : per_dir;
   const int rows = (a.B + slices - 1) / slices;
-  if (rows < 8 || rows > B3_RB * B3_MAX_CHUNKS) return false;
+  if (rows > B3_RB * B3_MAX_CHUNKS) return false;
   const int nch = (rows + B3_RB - 1) / B3_RB;
   // chunks of <= 8 rows (one n-tile each): the MMA work is proportional to the number of chunks, so as few as the rows need
   *slices_out = slices;

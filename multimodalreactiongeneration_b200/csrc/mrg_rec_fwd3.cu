@@ -25,8 +25,9 @@
 //    the tail reads one float4 per (row, unit)); the accumulator (gate row g / g + 8 x batch rows 2q, 2q + 1) is stored
 //    with a row stride of 132 floats: conflict free;
 //  * tail warp tw serves row tw of every chunk.
-// Used when the caller asks for a reduced-precision mode AND a cluster gets >= 8 rows (B >= 120 per direction): below
-// that the step is latency-bound and the FFMA2 kernel is as fast (rec_fwd2 stays).
+// Used whenever the caller asks for a reduced-precision mode at H = 256 and a cluster gets <= 64 rows: measured faster than
+// the FFMA2 kernel at every batch size (tools/rec_bench.py REDUCED=1, us per timestep forward / BPTT: B = 16 0.83 / 0.74 vs
+// 0.90 / 0.92, B = 64 0.94 / 0.83 vs 1.49 / 1.55, B = 128 1.32 / 1.16 vs 2.43 / 2.57, B = 256 1.98 / 1.75 vs 4.51 / 4.64).
 #include <cstddef>
 #include <cstdlib>
 
@@ -319,7 +320,7 @@ static int launch_fwd3(const RecArgs& a, int slices, int nch, cudaStream_t strea
   return 0;
 }
 
-// Does the tensor-core forward apply?  Reduced-precision call, H = 256, one wave of clusters with 8 .. 64 rows each (chunks of <= 8 rows).
+// Does the tensor-core forward apply?  Reduced-precision call, H = 256, one wave of clusters with <= 64 rows each (chunks of <= 8 rows).
 bool rec_forward_mma_applies(const RecArgs& a, int* slices_out, int* nch_out) {
   static int off = -1;
   if (off < 0) {
@@ -334,7 +335,7 @@ bool rec_forward_mma_applies(const RecArgs& a, int* slices_out, int* nch_out) {
   if (per_dir < 1) per_dir = 1;
   const int slices = a.B < per_dir ? a.B : per_dir;
   const int rows = (a.B + slices - 1) / slices;
-  if (rows < 8 || rows > F3_RB * F3_MAX_CHUNKS) return false;
+  if (rows > F3_RB * F3_MAX_CHUNKS) return false;
   const int nch = (rows + F3_RB - 1) / F3_RB;
   // chunks of <= 8 rows (one n-tile each): the MMA work is proportional to the number of chunks, so as few as the rows need
   *slices_out = slices;

@@ -393,10 +393,13 @@ def test_bf16_mode_within_stated_bound(I, H, L, bi, B, T):
 
 @pytest.mark.parametrize("mode,B,T,L,bi,with_hx", [("bf16", 256, 40, 2, False, True), ("tf32", 130, 25, 1, False, False),
                                                   ("bf16", 270, 12, 1, True, True), ("tf32", 600, 6, 1, False, True),
-                                                  ("tf32", 240, 9, 1, False, True), ("bf16", 120, 300, 1, False, False)])
+                                                  ("tf32", 240, 9, 1, False, True), ("bf16", 120, 300, 1, False, False),
+                                                  ("tf32", 7, 23, 2, False, True), ("tf32", 33, 11, 1, False, True),
+                                                  ("bf16", 64, 50, 1, True, True), ("tf32", 64, 300, 1, False, False)])
 def test_reduced_precision_tensor_core_recurrence(mode, B, T, L, bi, with_hx):
-    """In the reduced-precision modes a cluster with >= 8 rows runs h W_hh^T (rec_fwd3_kernel) and dpre W_hh
-    (rec_bwd3_kernel) on the warp-level tensor cores, one tf32 pass.  Same stated bound as the modes themselves (states
+    """In the reduced-precision modes an H = 256 layer runs h W_hh^T (rec_fwd3_kernel) and dpre W_hh (rec_bwd3_kernel) on
+    the warp-level tensor cores, one tf32 pass (chunks of <= 8 batch rows; the last four cases: one row per cluster on
+    7 clusters with two layers, 2-3 rows, both directions at the headline batch, the headline shape itself).  Same stated bound as the modes themselves (states
     2e-2 per step, gradients 5e-2) against fp64 nn.LSTM: 17-18 rows per cluster in two chunks, ragged 8-9 rows in one chunk,
     both directions (39 rows, three chunks), 40 rows in three chunks, a full 16-row m-tile in one chunk, 8 rows over the
     benchmark length, carried state with gradients at h_n / c_n and h_0 / c_0."""

@@ -34,7 +34,7 @@ if __name__ == "__main__":
     shapes = [(64, 300, 256, 1), (64, 300, 256, 2), (8, 300, 256, 1), (256, 300, 256, 1), (64, 300, 128, 1),
               (64, 300, 128, 2), (1024, 30, 256, 1), (16, 300, 256, 1), (32, 300, 256, 1)]
     if os.environ.get("REDUCED", "0") == "1":
-        shapes = [(64, 300, 256, 2), (128, 300, 256, 1), (240, 300, 256, 1), (256, 300, 256, 1), (256, 300, 256, 2)]
+        shapes = [(16, 300, 256, 1), (32, 300, 256, 1), (64, 300, 256, 1), (96, 300, 256, 1), (64, 300, 256, 2), (128, 300, 256, 1), (240, 300, 256, 1), (256, 300, 256, 1), (256, 300, 256, 2)]
     for (B, T, H, D) in shapes:
         row = f"B={B:5d} T={T} H={H} D={D}:"
         variants = (("cluster", 0),) if os.environ.get("REDUCED", "0") != "1" else (("fp32", 0), ("tf32-mode", _cabi.F_TF32))
