@@ -53,7 +53,7 @@ extern "C" {
 #define MRG_F_ACCUMULATE   8   /* backward: add into dw_ih / dw_hh / db instead of overwriting  */
 #define MRG_F_TF32        32   /* reduced-precision mode: the projection GEMMs run ONE tf32 tensor-core
                                   pass (10-bit mantissa, >= bf16 precision) instead of the 3-pass
-                                  fp32-grade split.  H = 256 layers whose clusters get 8..48 batch rows
+                                  fp32-grade split.  H = 256 layers (<= 48 batch rows per cluster)
                                   also run h W_hh^T / dpre W_hh as one tf32 pass on the warp-level tensor
                                   cores (csrc/mrg_rec_fwd3.cu, mrg_rec_bwd3.cu); states, cell and
                                   accumulation stay fp32.  Bound: 2e-2 per step / 5e-2 on gradients   */
