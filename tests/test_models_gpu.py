@@ -519,7 +519,8 @@ def test_gru_matches_torch_gru(I, H, L, bi, B, T, with_hx):
         assert rel_l2(hm.grad.cpu(), hr.grad) <= GRAD_TOL
 
 
-@pytest.mark.parametrize("mode,B,T,bi", [("tf32", 256, 30, False), ("bf16", 150, 17, True), ("tf32", 128, 40, False)])
+@pytest.mark.parametrize("mode,B,T,bi", [("tf32", 256, 30, False), ("bf16", 150, 17, True), ("tf32", 128, 40, False),
+                                         ("tf32", 20, 15, True), ("bf16", 64, 300, False)])
 def test_gru_reduced_precision_tensor_core_recurrence(mode, B, T, bi):
     """GRU variant of the tensor-core recurrent kernels (rec_fwd3 / rec_bwd3_kernel<256, gru>) in the reduced-precision
     modes: fp64 nn.GRU, the modes' stated bound (states 2e-2, gradients 5e-2), carried state, both directions."""
