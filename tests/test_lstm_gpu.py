@@ -395,7 +395,8 @@ def test_bf16_mode_within_stated_bound(I, H, L, bi, B, T):
                                                   ("bf16", 270, 12, 1, True, True), ("tf32", 600, 6, 1, False, True),
                                                   ("tf32", 240, 9, 1, False, True), ("bf16", 120, 300, 1, False, False),
                                                   ("tf32", 7, 23, 2, False, True), ("tf32", 33, 11, 1, False, True),
-                                                  ("bf16", 64, 50, 1, True, True), ("tf32", 64, 300, 1, False, False)])
+                                                  ("bf16", 64, 50, 1, True, True), ("tf32", 64, 300, 1, False, False),
+                                                  ("tf32", 40, 1, 1, False, True), ("bf16", 40, 2, 1, True, True)])
 def test_reduced_precision_tensor_core_recurrence(mode, B, T, L, bi, with_hx):
     """In the reduced-precision modes an H = 256 layer runs h W_hh^T (rec_fwd3_kernel) and dpre W_hh (rec_bwd3_kernel) on
     the warp-level tensor cores, one tf32 pass (chunks of <= 8 batch rows; the last four cases: one row per cluster on
