@@ -5,6 +5,7 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
   --config 2 (default)  simple_lstm fp32 training step, B=64/GPU x T=300          [BASELINE configs[1], the headline]
+                        (--precision tf32|bf16 times the same step in a reduced-precision mode and labels it so)
   --config 3            lstm_with_sampling, scheduled-sampling rollout training, B=64/GPU x T=900, DDP     [configs[2]]
   --config 4            lstmformer training step, B=256/GPU x T=300, --precision bf16|tf32|fp32           [configs[3]]
   --config 5            streaming generation, 1024 dyads, one frame per call: p50 / p99 latency           [configs[4]]
@@ -354,6 +355,12 @@ def run_cfg2(args):
     from multimodalreactiongeneration_b200.mr_gen.model.simple_lstm.simple_lstm import SimpleLSTM
     from multimodalreactiongeneration_b200.mr_gen.tainer.trainer import Trainer
     _cabi, world, rank, local_rank, dev = _setup()
+    # the headline is the fp32 mode (parity <= 1e-5 / 1e-4); --precision tf32|bf16 (or MRG_PRECISION) times the same step
+    # in a reduced-precision mode and says so in `dtype` / `config`
+    from multimodalreactiongeneration_b200 import lstm as _lstm_mod, set_precision
+    if args.precision != "fp32":
+        set_precision(args.precision)
+    mode = _lstm_mod._PRECISION["mode"]
 
     torch.manual_seed(0)
     model = SimpleLSTM(*simple_lstm_cfg(HIDDEN, LAYERS, False, ACOUSTIC, POSE)).to(dev)
@@ -444,9 +451,12 @@ def run_cfg2(args):
     line = {
         "metric": "train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[mode],
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[2], "global_batch": world * B_PER_GPU, "frames_per_step": frames,
+        "config": {"workload": WORKLOADS[2] if mode == "fp32" else
+                   WORKLOADS[2].replace("fp32 train step", f"train step in the {mode} reduced-precision mode (NOT the fp32 headline)"),
+                   "precision": mode, "global_batch": world * B_PER_GPU, "frames_per_step": frames,
                    "parallelism": f"dp{world} (batch sharded by sequence; flat gradient bucket, decoder / attention slices "
                                   f"all-reduced during the encoders' BPTT, the rest in one trailing all-reduce)",
                    "cuda_graph": graph_note,
@@ -623,8 +633,9 @@ def run_cfg4(args):
     dtype = {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision]
     out = _nx_train_bench(args, 4, lambda rank: Metaformer(*metaformer_cfg()), dtype,
                           {"precision": args.precision,
-                           "precision_note": "fp32: 3xTF32 tensor-core GEMMs (fp32-grade); tf32: one tensor-core pass per "
-                                             "GEMM; the recurrence accumulates in fp32 in every mode"})
+                           "precision_note": "fp32: 3xTF32 tensor-core GEMMs and exact fp32 recurrence (fp32-grade); tf32 / bf16: "
+                                             "one tf32 tensor-core pass per GEMM and per recurrent product; accumulation, cell "
+                                             "and hidden states are fp32 in every mode"})
     if out is None:
         return
     line = out[0]
@@ -735,7 +746,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="cfg 4 GEMM precision mode")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"], help="precision mode (cfg 2: fp32 is the headline; cfg 4: BASELINE names bf16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of "

@@ -80,7 +80,9 @@ def set_precision(mode: str) -> None:
     d(pre-activations) that feed the backward GEMMs are 4 x bf16 per hidden unit (8 bytes instead of 16), the GEMMs
     next to them write / read bfloat16 directly (bf16 values are exact tf32 operands) — for the cluster kernels
     (H in {128, 256}, T > 1); other shapes run as in "tf32".  Same stated bound: states 2e-2, loss / gradients 5e-2
-    norm-relative.  Accumulation (TMEM) and the recurrence (h W_hh, cell state, hidden states) stay fp32 in every mode."""
+    norm-relative.  In both reduced modes an H = 256 layer also runs the recurrent products h W_hh^T / dpre W_hh as one tf32
+    pass on the warp-level tensor cores (csrc/mrg_rec_fwd3.cu, mrg_rec_bwd3.cu); accumulation (TMEM / MMA accumulators),
+    cell state and hidden states stay fp32 in every mode, and the "fp32" recurrence is exact fp32 (FFMA2)."""
     if mode not in ("fp32", "tf32", "bf16"):
         raise ValueError("precision must be 'fp32', 'tf32' or 'bf16'")
     _PRECISION["mode"] = mode
