@@ -451,6 +451,39 @@ def test_reduced_precision_tensor_core_recurrence(mode, B, T, L, bi, with_hx):
         assert v <= BF16_GRAD_TOL, (k, v)
 
 
+@pytest.mark.parametrize("mode,B,bi", [("tf32", 256, False), ("bf16", 64, True), ("tf32", 100, False)])
+def test_tensor_core_recurrence_is_deterministic(mode, B, bi):
+    """The mbarrier / st.async hand-offs of rec_fwd3 / rec_bwd3 have no sanitizer evidence on this pool: five runs of the same
+    forward + backward (1, 2 and 3 chunks per cluster, both directions) must be bit-identical in every output and gradient
+    (fixed-order sums everywhere; a lost or early hand-off would show as a different bit pattern)."""
+    import multimodalreactiongeneration_b200 as pkg
+    H, T = 256, 120
+    _, mine = _build(H, H, 2, bi)
+    D = 2 if bi else 1
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, T, H, generator=g).cuda()
+    hx = (torch.randn(2 * D, B, H, generator=g).cuda() * 0.5, torch.randn(2 * D, B, H, generator=g).cuda() * 0.5)
+    w = torch.randn(B, T, D * H, generator=g).cuda()
+    runs = []
+    try:
+        pkg.set_precision(mode)
+        for _ in range(5):
+            for p in mine.parameters():
+                p.grad = None
+            xm = x.clone().requires_grad_(True)
+            hm = tuple(t.clone().requires_grad_(True) for t in hx)
+            ym, (hn, cn) = mine(xm, hm)
+            ((ym * w).sum() + hn.sum() - cn.sum()).backward()
+            torch.cuda.synchronize()
+            runs.append([ym.detach().clone(), hn.detach().clone(), cn.detach().clone(), xm.grad.clone(), hm[0].grad.clone(),
+                         hm[1].grad.clone()] + [p.grad.clone() for p in mine.parameters()])
+    finally:
+        pkg.set_precision("fp32")
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b)
+
+
 def test_bf16_mode_falls_back_to_fp32_reserve_on_generic_shapes():
     """Shapes the cluster kernels do not cover (H=32: generic kernels; T=1: pointwise cell) keep the fp32 reserve in
     bf16 mode (documented in set_precision) and stay inside the bound."""
