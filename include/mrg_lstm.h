@@ -71,6 +71,10 @@ extern "C" {
                                   independent LSTM stacks (audio / motion encoders) run side by side on two streams */
 #define MRG_F_ACC_WEIGHTS 256  /* backward: add into dw_ih / dw_hh only (db is overwritten): weight gradients that
                                   accumulate straight into the trainer's flat gradient bucket            */
+#define MRG_F_PACK_VALID  512  /* forward: `w_pack` and the first two regions of `workspace` (bias pack, and the W_hh pack
+                                  of the T == 1 carried-state path) still hold what an earlier call with the SAME weights,
+                                  shape, `w_pack` and `workspace` wrote — the pack launch is skipped (frame-by-frame
+                                  inference with frozen weights; the caller owns both buffers and the invalidation)    */
 #define MRG_F_BWD_NO_WGRAD   2048  /* backward: BPTT + bias sums + dX only (leaves d(pre-activations) in `gates`)    */
 #define MRG_F_BWD_WGRAD_ONLY 4096  /* backward: only dW_ih / dW_hh from a previous NO_WGRAD call (any stream)        */
 #define MRG_F_ZERO_STATE  16   /* caller guarantees h0 = c0 = 0 (hx=None): with T == 1 the layer is a

@@ -13,6 +13,7 @@ F_ACC_WEIGHTS = 256
 F_BF16 = 64
 F_GRU = 128
 F_BWD_NO_WGRAD, F_BWD_WGRAD_ONLY = 2048, 4096
+F_PACK_VALID = 512
 
 EXPORTS = (
     "mrg_version", "mrg_last_error_string", "mrg_device_info", "mrg_lstm_workspace_bytes",

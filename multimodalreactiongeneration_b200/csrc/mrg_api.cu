@@ -123,7 +123,10 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   }
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
 
-  if (int e = pack_weights(w, w_pack, bias_pack, whh_pack, I, H, D, stream)) return e;
+  // MRG_F_PACK_VALID: w_pack and the head of the workspace (bias pack, W_hh pack of the single-step path) still hold the
+  // packs an earlier call with the same weights, shape and buffers wrote (inference with frozen weights): skip the launch
+  if (!(flags & MRG_F_PACK_VALID))
+    if (int e = pack_weights(w, w_pack, bias_pack, whh_pack, I, H, D, stream)) return e;
   const size_t slot = (size_t)B * H;
   for (int d = 0; d < D; ++d) {
     float* ys = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : (size_t)T * slot);

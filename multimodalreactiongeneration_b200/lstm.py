@@ -23,6 +23,8 @@ from torch.nn import functional as F
 from . import _cabi
 
 _WORKSPACES = {}
+_F_INFER = 1 << 30   # host-only flag bit of _LSTMLayerFn (never reaches the C-ABI): the call runs under torch.no_grad()
+_PACK_CACHE = {}   # (weight storages, shape, flags) -> (weights, versions, w_pack, dedicated workspace): see _LSTMLayerFn.forward
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -153,16 +155,41 @@ class _LSTMLayerFn(torch.autograd.Function):
         x = _cabi.contiguous3(x)
         T, B, I = x.shape
         dev = x.device
-        need_grad = any(ctx.needs_input_grad)
+        # needs_input_grad is True for the parameters even under torch.no_grad(); the caller (B200LSTM.forward) reads the grad
+        # mode where it is visible and passes it as a host-only flag bit
+        infer = bool(flags & _F_INFER)
+        flags &= ~_F_INFER
+        need_grad = any(ctx.needs_input_grad) and not infer
         opts = dict(dtype=torch.float32, device=dev)
         if flags & _cabi.F_BF16 and not (T > 1 and H in (128, 256) and not flags & _cabi.F_GENERIC_REC):
             flags &= ~_cabi.F_BF16      # bf16 reserve: cluster kernels only; other shapes keep the fp32 reserve
         gates = torch.empty((D, T, B, H, 4), dtype=torch.bfloat16 if flags & _cabi.F_BF16 else torch.float32, device=dev)
         y_ext = torch.empty((D, T + 1, B, H), **opts)
         c_ext = torch.empty((D, T + 1, B, H), **opts)
-        w_pack = torch.empty((L.mrg_lstm_pack_floats(I, H, D),), **opts)   # W_ih: raw | tf32 hi | lo planes
         nbytes = L.mrg_lstm_workspace_bytes(T, B, I, H, D)
-        ws = _workspace(dev, nbytes)
+        # Inference with frozen weights (no gradient wanted, plain LSTM parameters): the weight packs of a (layer, shape) are
+        # written once into buffers this cache owns and reused until a weight changes (version counter / storage) —
+        # frame-by-frame generation otherwise re-packs every layer on every frame (StreamingGenerator: 5 launches of 3 us).
+        pack_key = pack_hit = None
+        if not need_grad and not (flags & _cabi.F_GRU):
+            pack_key = (tuple(0 if t is None else t.data_ptr() for t in weights), T, B, I, H, D, flags, dev.index)
+            ent = _PACK_CACHE.get(pack_key)
+            # same storages (the key; the entry keeps its tensors alive, so an address cannot be recycled) and unchanged
+            # version counters (shared by every alias of a parameter: optimizer steps and load_state_dict bump them)
+            if ent is not None and all(a is None or a._version == v for a, v in zip(weights, ent[1])):
+                pack_hit = ent
+        if pack_hit is not None:
+            w_pack, ws = pack_hit[2], pack_hit[3]
+            flags |= _cabi.F_PACK_VALID
+        elif pack_key is not None:
+            w_pack = torch.empty((L.mrg_lstm_pack_floats(I, H, D),), **opts)
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+            if len(_PACK_CACHE) >= 64:
+                _PACK_CACHE.clear()
+            _PACK_CACHE[pack_key] = (tuple(weights), tuple(0 if t is None else t._version for t in weights), w_pack, ws)
+        else:
+            w_pack = torch.empty((L.mrg_lstm_pack_floats(I, H, D),), **opts)   # W_ih: raw | tf32 hi | lo planes
+            ws = _workspace(dev, nbytes)
         dw = (_cabi.DirWeights * D)()
         keep = []
         for d in range(D):
@@ -323,6 +350,8 @@ class B200LSTM(nn.LSTM):
             if tuple(h0.shape) != want or tuple(c0.shape) != want:
                 raise RuntimeError(f"Expected hidden size {want}, got {tuple(h0.shape)} / {tuple(c0.shape)}")
         flags = _default_flags()
+        if not torch.is_grad_enabled():
+            flags |= _F_INFER     # inference: no reserve for a backward, cached weight packs
         hs, cs = [], []
         for layer in range(self.num_layers):
             h0l = None if hx is None else hx[0][layer * D:(layer + 1) * D]

@@ -271,6 +271,41 @@ def test_presplit_weight_gemm(a_mn, b_mn, M, N, K, acc, flags):
                                     c.data_ptr(), N, 64, N, K, 0, None, 0, 0, st) != 0
 
 
+@pytest.mark.parametrize("T", [1, 7])
+def test_inference_reuses_weight_packs_until_a_weight_changes(T):
+    """Without gradients the weight packs of a layer are cached (MRG_F_PACK_VALID): the second call launches fewer kernels
+    and returns the same bits; an in-place weight update invalidates the cache (parity against fp64 nn.LSTM afterwards)."""
+    from multimodalreactiongeneration_b200 import _cabi
+    H, B = 256, 48
+    ref, mine = _build(64, H, 2, False)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, T, 64, generator=g, dtype=torch.double)
+    hx = (torch.randn(2, B, H, generator=g, dtype=torch.double) * 0.5, torch.randn(2, B, H, generator=g, dtype=torch.double) * 0.5)
+    xm, hm = x.float().cuda(), tuple(t.float().cuda() for t in hx)
+    with torch.no_grad():
+        l0 = _cabi.launch_count()
+        y1, _ = mine(xm, hm)
+        l1 = _cabi.launch_count()
+        y2, (h2, c2) = mine(xm, hm)
+        l2 = _cabi.launch_count()
+        assert (l2 - l1) < (l1 - l0)          # the pack launches are gone
+        assert torch.equal(y1, y2)
+        yr, (hr, cr) = ref(x, hx)
+        assert _per_step_err(y2, yr) <= STATE_TOL
+        for pm, pr in zip(mine.parameters(), ref.parameters()):   # in-place update: version counters move
+            pm.mul_(1.25)
+            pr.mul_(1.25)
+        y3, (h3, c3) = mine(xm, hm)
+        yr3, (hr3, cr3) = ref(x, hx)
+        assert _per_step_err(y3, yr3) <= STATE_TOL
+        assert rel_err(h3.cpu(), hr3) <= STATE_TOL and rel_err(c3.cpu(), cr3) <= STATE_TOL
+    # with gradients the cache is bypassed
+    xg = xm.clone().requires_grad_(True)
+    yg, _ = mine(xg, hm)
+    yg.sum().backward()
+    assert xg.grad is not None
+
+
 @pytest.mark.parametrize("H,bi", [(256, False), (32, True)])
 def test_single_step_zero_state_pointwise_path(H, bi):
     """T == 1 with hx=None takes the pointwise cell kernels (no recurrence); must equal torch.nn.LSTM."""
