@@ -128,7 +128,12 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   if (!(flags & MRG_F_PACK_VALID))
     if (int e = pack_weights(w, w_pack, bias_pack, whh_pack, I, H, D, stream)) return e;
   const size_t slot = (size_t)B * H;
-  for (int d = 0; d < D; ++d) {
+  // single-step inference: nobody reads the init slots — a zero-state step needs none, a carried-state step takes h0 / c0
+  // straight from the caller's tensors (no staging copy); training keeps them (the backward reads h_{-1}, c_{-1} there)
+  bool direct_state = single_state && !(flags & MRG_F_TRAIN);
+  for (int d = 0; d < D; ++d) direct_state = direct_state && w[d].h0 && w[d].c0;
+  const bool skip_init = (single_zero && !(flags & MRG_F_TRAIN)) || direct_state;
+  for (int d = 0; d < D && !skip_init; ++d) {
     float* ys = y_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : (size_t)T * slot);
     float* cs = c_ext + (size_t)d * (T + 1) * slot + (d == 0 ? 0 : (size_t)T * slot);
     if (w[d].h0) MRG_CUDA_CHECK(cudaMemcpyAsync(ys, w[d].h0, slot * sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -156,13 +161,15 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     // gates += h0 * W_hh^T (second projection), then the pointwise cell with the carried c0
     for (int d = 0; d < D; ++d) {
       GemmArgs g = {};
-      g.a = y_ext + (size_t)d * 2 * slot + (d == 0 ? 0 : slot); g.a_sm = H; g.a_sk = 1;
+      g.a = direct_state ? w[d].h0 : y_ext + (size_t)d * 2 * slot + (d == 0 ? 0 : slot); g.a_sm = H; g.a_sk = 1;
       g.b = whh_pack + (size_t)d * 4 * H * H; g.b_sk = 1; g.b_sn = H;
       g.c = gates + (size_t)d * B * 4 * H; g.ldc = 4 * H;
       g.M = B; g.N = 4 * H; g.K = H; g.accumulate = 1;
       if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
     }
-    return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, (flags & MRG_F_TRAIN) ? 1 : 0, 1, stream);
+    return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, (flags & MRG_F_TRAIN) ? 1 : 0, 1, stream,
+                                   direct_state ? w[0].c0 : nullptr,
+                                   direct_state && D > 1 ? w[1].c0 : nullptr);
   }
   RecArgs r = {};
   r.gates = gates;

@@ -321,7 +321,7 @@ int rec2_max_chunks(int H, int rbc);
 void pick_partition2(int H, int B, int D, int budget, int* slices_out, int* nch_out, int* rbc_out);
 
 int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
-                            int has_state, cudaStream_t stream);
+                            int has_state, cudaStream_t stream, const float* c0_d0 = nullptr, const float* c0_d1 = nullptr);
 int cell_zero_state_backward(float* gates, const float* c_ext, const float* dy, const float* dh_n,
                              const float* dc_n, float* db_part, int B, int H, int D, cudaStream_t stream);
 

@@ -172,7 +172,8 @@ int colsum_deinterleave(const float* part, float* db, int B, int H, int accumula
 // reference's rollout.  One thread per (direction, row, unit).
 // ---------------------------------------------------------------------------------------------
 __global__ void cell_zero_fwd_kernel(float* __restrict__ gates, float* __restrict__ y_ext,
-                                     float* __restrict__ c_ext, int B, int H, int D, int train, int has_state) {
+                                     float* __restrict__ c_ext, int B, int H, int D, int train, int has_state,
+                                     const float* __restrict__ c0_d0, const float* __restrict__ c0_d1) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_dir = (long long)B * H;
   if (idx >= per_dir * D) return;
@@ -184,7 +185,10 @@ __global__ void cell_zero_fwd_kernel(float* __restrict__ gates, float* __restric
   const long long out = (long long)d * 2 * per_dir + (d == 0 ? per_dir : 0) + r;  // dir0: slot 1, dir1: slot 0
   const long long init = (long long)d * 2 * per_dir + (d == 0 ? 0 : per_dir) + r; // the other slot holds c0
   float c = gi * gg;
-  if (has_state) c = fmaf(gf, c_ext[init], c);  // carried state: the h0 * W_hh term is already in `gates`
+  if (has_state) {  // carried state: the h0 * W_hh term is already in `gates`; c0 from the caller's tensor (inference: no
+    const float* c0 = d == 0 ? c0_d0 : c0_d1;   // staging copy) or from the init slot of c_ext
+    c = fmaf(gf, c0 ? c0[r] : c_ext[init], c);
+  }
   const float h = go * tanhf(c);
   y_ext[out] = h;
   c_ext[out] = c;
@@ -215,12 +219,12 @@ __global__ void cell_zero_bwd_kernel(float* __restrict__ gates, const float* __r
 }
 
 int cell_zero_state_forward(float* gates, float* y_ext, float* c_ext, int B, int H, int D, int train,
-                            int has_state, cudaStream_t stream) {
+                            int has_state, cudaStream_t stream, const float* c0_d0, const float* c0_d1) {
   const long long n = (long long)B * H * D;
   ProfScope prof(PROF_REC_FWD, stream);
   count_launch();
   cell_zero_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gates, y_ext, c_ext, B, H, D, train,
-                                                                        has_state);
+                                                                        has_state, c0_d0, c0_d1);
   MRG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
