@@ -1,6 +1,7 @@
 // C-ABI entry points (include/mrg_lstm.h): orchestration of pack -> projection GEMM -> recurrent
 // kernel for the forward, and recurrent BPTT kernel -> dX / dW GEMMs -> bias column sums for the
 // backward.  Everything is queued on the caller's stream; nothing synchronises.
+#include <cstdint>
 #include <cstdlib>
 
 #include "mrg_common.cuh"
@@ -71,8 +72,15 @@ extern "C" size_t mrg_lstm_workspace_bytes(int T, int B, int I, int H, int D) {
   if (T < 0 || B <= 0 || I <= 0 || H <= 0 || D < 1 || D > 2) return 0;
   const size_t head = align_up((size_t)D * 4 * H * sizeof(float), 256) +
                       align_up((size_t)D * B * 4 * H * sizeof(float), 256) +
-                      (T == 1 ? align_up((size_t)D * 4 * H * H * sizeof(float), 256) : 0);
+                      (T == 1 ? align_up((size_t)D * 4 * H * H * sizeof(float), 256) +
+                                    align_up((size_t)D * 4 * H * (I + H) * sizeof(float), 256) +   // [W_ih | W_hh] pack
+                                    align_up((size_t)D * B * (I + H) * sizeof(float), 256)         // [x | h0] staging
+                              : 0);
   size_t g = gemm_ws(T * B, 4 * H, I);
+  if (T == 1) {
+    const size_t m = gemm_ws(B, 4 * H, I + H);
+    if (m > g) g = m;
+  }
   size_t v = gemm_ws(T * B, I, 4 * H);
   if (v > g) g = v;
   v = gemm_ws(4 * H, I, T * B);
@@ -117,16 +125,22 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
   for (int d = 0; d < D; ++d) single_zero = single_zero && !w[d].h0 && !w[d].c0;
   const bool single_state = (T == 1) && !single_zero;
   float* whh_pack = nullptr;
+  float* wcat_pack = nullptr;   // single-step inference with carried state: ONE projection over [x | h0] (below)
+  float* xh = nullptr;
   if (T == 1) {
     if (single_state) whh_pack = (float*)ws;
     ws += align_up((size_t)D * 4 * H * H * sizeof(float), 256);
+    if (single_state) wcat_pack = (float*)ws;
+    ws += align_up((size_t)D * 4 * H * (I + H) * sizeof(float), 256);
+    xh = (float*)ws;
+    ws += align_up((size_t)D * B * (I + H) * sizeof(float), 256);
   }
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
 
   // MRG_F_PACK_VALID: w_pack and the head of the workspace (bias pack, W_hh pack of the single-step path) still hold the
   // packs an earlier call with the same weights, shape and buffers wrote (inference with frozen weights): skip the launch
   if (!(flags & MRG_F_PACK_VALID))
-    if (int e = pack_weights(w, w_pack, bias_pack, whh_pack, I, H, D, stream)) return e;
+    if (int e = pack_weights(w, w_pack, bias_pack, whh_pack, I, H, D, stream, wcat_pack)) return e;
   const size_t slot = (size_t)B * H;
   // single-step inference: nobody reads the init slots — a zero-state step needs none, a carried-state step takes h0 / c0
   // straight from the caller's tensors (no staging copy); training keeps them (the backward reads h_{-1}, c_{-1} there)
@@ -142,6 +156,26 @@ extern "C" int mrg_lstm_layer_forward(const float* x, const mrg_lstm_dir_weights
     else MRG_CUDA_CHECK(cudaMemsetAsync(cs, 0, slot * sizeof(float), stream));
   }
   if (T == 0) return 0;
+  // carried-state single step in inference: gates = [x | h0] . [W_ih | W_hh]^T + b as ONE GEMM (the two-GEMM form below
+  // pays launch + fill + drain twice, and the second one reads the output back to accumulate)
+  if (direct_state && I % 4 == 0 && H % 4 == 0 && ((uintptr_t)x & 15) == 0) {
+    bool aligned = true;
+    for (int d = 0; d < D; ++d) aligned = aligned && ((uintptr_t)w[d].h0 & 15) == 0;
+    if (aligned) {
+      for (int d = 0; d < D; ++d) {
+        float* a_cat = xh + (size_t)d * B * (I + H);
+        if (int e = concat_xh(x, w[d].h0, a_cat, B, I, H, stream)) return e;
+        GemmArgs g = {};
+        g.a = a_cat; g.a_sm = I + H; g.a_sk = 1;
+        g.b = wcat_pack + (size_t)d * 4 * H * (I + H); g.b_sk = 1; g.b_sn = I + H;
+        g.bias = bias_pack + (size_t)d * 4 * H;
+        g.c = gates + (size_t)d * B * 4 * H; g.ldc = 4 * H;
+        g.M = B; g.N = 4 * H; g.K = I + H;
+        if (int e = run_gemm(g, ws, ws_left, flags, stream)) return e;
+      }
+      return cell_zero_state_forward(gates, y_ext, c_ext, B, H, D, 0, 1, stream, w[0].c0, D > 1 ? w[1].c0 : nullptr);
+    }
+  }
   for (int d = 0; d < D; ++d) {
     GemmArgs g = {};
     g.a = x; g.a_sm = I; g.a_sk = 1;

@@ -272,7 +272,8 @@ size_t gemm_simt_workspace_bytes(int M, int N, int K);
 
 // w_pack: three planes of [D][4H][I] floats — gate-interleaved W_ih as is, its tf32 hi part, its lo part (x - hi)
 int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, float* whh_pack, int I, int H,
-                 int D, cudaStream_t stream);
+                 int D, cudaStream_t stream, float* wcat_pack = nullptr);
+int concat_xh(const float* x, const float* h, float* dst, int B, int I, int H, cudaStream_t stream);
 
 struct RecArgs {
   float* gates;        // [D][T][B][H][4]

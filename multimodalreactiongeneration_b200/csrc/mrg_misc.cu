@@ -53,7 +53,7 @@ struct PackArgs {
 };
 
 __global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __restrict__ bias_pack,
-                            float* __restrict__ whh_pack, int I, int H) {
+                            float* __restrict__ whh_pack, float* __restrict__ wcat_pack, int I, int H) {
   const int d = blockIdx.y;
   const int row = blockIdx.x;  // packed row j*4+g
   const int j = row >> 2, g = row & 3;
@@ -72,6 +72,12 @@ __global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __res
     float* hd = whh_pack + ((size_t)d * 4 * H + row) * H;
     for (int i = threadIdx.x; i < H; i += blockDim.x) hd[i] = hs[i];
   }
+  if (wcat_pack != nullptr) {  // single-step inference: [W_ih | W_hh] rows for ONE projection GEMM over [x | h0]
+    const float* hs = p.w_hh[d] + (size_t)(g * H + j) * H;
+    float* cd = wcat_pack + ((size_t)d * 4 * H + row) * (I + H);
+    for (int i = threadIdx.x; i < I; i += blockDim.x) cd[i] = src[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) cd[I + i] = hs[i];
+  }
   if (threadIdx.x == 0 && bias_pack != nullptr) {
     float b = 0.f;
     if (p.b_ih[d]) b += p.b_ih[d][g * H + j];
@@ -80,8 +86,31 @@ __global__ void pack_kernel(PackArgs p, float* __restrict__ w_pack, float* __res
   }
 }
 
+// dst[b][0 .. I) = x[b][0 .. I), dst[b][I .. I + H) = h[b][0 .. H): the A operand of the merged single-step projection
+__global__ void concat_xh_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ dst, int B,
+                                 int I4, int H4) {
+  const int W4 = I4 + H4;
+  const long long total = (long long)B * W4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W4);
+    const long long b = i / W4;
+    reinterpret_cast<float4*>(dst)[i] = c < I4 ? __ldg(reinterpret_cast<const float4*>(x) + b * I4 + c)
+                                               : __ldg(reinterpret_cast<const float4*>(h) + b * H4 + (c - I4));
+  }
+}
+
+int concat_xh(const float* x, const float* h, float* dst, int B, int I, int H, cudaStream_t stream) {
+  const long long total = (long long)B * ((I + H) / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launch();
+  concat_xh_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, h, dst, B, I / 4, H / 4);
+  MRG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack, float* whh_pack, int I, int H,
-                 int D, cudaStream_t stream) {
+                 int D, cudaStream_t stream, float* wcat_pack) {
   PackArgs p;
   for (int d = 0; d < 2; ++d) {
     p.w_hh[d] = d < D ? w[d].w_hh : nullptr;
@@ -90,7 +119,7 @@ int pack_weights(const mrg_lstm_dir_weights* w, float* w_pack, float* bias_pack,
     p.b_hh[d] = d < D ? w[d].b_hh : nullptr;
   }
   dim3 grid(4 * H, D);
-  pack_kernel<<<grid, 128, 0, stream>>>(p, w_pack, bias_pack, whh_pack, I, H);
+  pack_kernel<<<grid, 128, 0, stream>>>(p, w_pack, bias_pack, whh_pack, wcat_pack, I, H);
   MRG_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return 0;
