@@ -271,16 +271,20 @@ def test_presplit_weight_gemm(a_mn, b_mn, M, N, K, acc, flags):
                                     c.data_ptr(), N, 64, N, K, 0, None, 0, 0, st) != 0
 
 
-@pytest.mark.parametrize("T", [1, 7])
-def test_inference_reuses_weight_packs_until_a_weight_changes(T):
+@pytest.mark.parametrize("T,bi", [(1, False), (7, False), (1, True)])
+def test_inference_reuses_weight_packs_until_a_weight_changes(T, bi):
     """Without gradients the weight packs of a layer are cached (MRG_F_PACK_VALID): the second call launches fewer kernels
-    and returns the same bits; an in-place weight update invalidates the cache (parity against fp64 nn.LSTM afterwards)."""
+    and returns the same bits; an in-place weight update invalidates the cache (parity against fp64 nn.LSTM afterwards).
+    T = 1 with carried state is the streaming step: one projection GEMM over [x | h0], h0 / c0 read in place (both directions
+    in the third case)."""
     from multimodalreactiongeneration_b200 import _cabi
     H, B = 256, 48
-    ref, mine = _build(64, H, 2, False)
+    ref, mine = _build(64, H, 2, bi)
+    D = 2 if bi else 1
     g = torch.Generator().manual_seed(21)
     x = torch.randn(B, T, 64, generator=g, dtype=torch.double)
-    hx = (torch.randn(2, B, H, generator=g, dtype=torch.double) * 0.5, torch.randn(2, B, H, generator=g, dtype=torch.double) * 0.5)
+    hx = (torch.randn(2 * D, B, H, generator=g, dtype=torch.double) * 0.5,
+          torch.randn(2 * D, B, H, generator=g, dtype=torch.double) * 0.5)
     xm, hm = x.float().cuda(), tuple(t.float().cuda() for t in hx)
     with torch.no_grad():
         l0 = _cabi.launch_count()
