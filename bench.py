@@ -631,6 +631,9 @@ def run_cfg4(args):
     from multimodalreactiongeneration_b200.mr_gen.model.lstmformer.lstmformer import Metaformer
     set_precision(args.precision)
     dtype = {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision]
+    # this eager step (700 launches, side streams, a caching allocator still growing its pools) settles after ~10 steps:
+    # with 3-5 warm-up steps the resident figure reads 5-15 % high (profiles/r2_final_validation.txt)
+    args.warmup = max(args.warmup, 10)
     out = _nx_train_bench(args, 4, lambda rank: Metaformer(*metaformer_cfg()), dtype,
                           {"precision": args.precision,
                            "precision_note": "fp32: 3xTF32 tensor-core GEMMs and exact fp32 recurrence (fp32-grade); tf32 / bf16: "
