@@ -223,6 +223,10 @@ class _LSTMLayerFn(torch.autograd.Function):
             ctx.saved = (x, gates, y_ext, c_ext, w_pack, weights, h0 is not None, c0 is not None)
             ctx.dims = (T, B, I, H, D, flags)
             ctx.consumed = False
+            # version-counter guard: with one direction y / h_n / c_n are VIEWS of the buffers the backward reads (y_ext,
+            # c_ext) — an in-place edit of an output (or of the input) between forward and backward must raise, not
+            # silently corrupt the gradients
+            ctx.save_for_backward(*((x, y, c_n) if D == 1 else (x,)))
         return y, h_n, c_n
 
     @staticmethod
@@ -231,6 +235,7 @@ class _LSTMLayerFn(torch.autograd.Function):
             raise RuntimeError("B200LSTM backward ran twice on the same graph: the reserve (gates) is "
                                "overwritten in place by d(pre-activations); retain_graph is not supported")
         ctx.consumed = True
+        _ = ctx.saved_tensors   # raises if x / y / c_n were modified in place since the forward
         L = _cabi.lib()
         x, gates, y_ext, c_ext, w_pack, weights, has_h0, has_c0 = ctx.saved
         T, B, I, H, D, flags = ctx.dims

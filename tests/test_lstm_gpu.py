@@ -271,6 +271,19 @@ def test_presplit_weight_gemm(a_mn, b_mn, M, N, K, acc, flags):
                                     c.data_ptr(), N, 64, N, K, 0, None, 0, 0, st) != 0
 
 
+def test_inplace_edit_of_an_output_before_backward_raises():
+    """y / h_n / c_n are views of the buffers the backward reads: editing one in place must raise (autograd's version
+    counters), not corrupt the gradients silently."""
+    _, mine = _build(32, 256, 1, False)
+    x = torch.randn(4, 6, 32, device="cuda", requires_grad=True)
+    y, (h, c) = mine(x)
+    loss = y.sum()
+    with torch.no_grad():
+        c.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        loss.backward()
+
+
 @pytest.mark.parametrize("T,bi", [(1, False), (7, False), (1, True)])
 def test_inference_reuses_weight_packs_until_a_weight_changes(T, bi):
     """Without gradients the weight packs of a layer are cached (MRG_F_PACK_VALID): the second call launches fewer kernels
