@@ -23,7 +23,7 @@ from torch.nn import functional as F
 
 from . import _cabi
 from .linear import _colsum, _gemm, fused_grad_target
-from .lstm import _LSTMLayerFn, _default_flags
+from .lstm import _F_INFER, _LSTMLayerFn, _default_flags
 
 
 def _four_gate_weights(w_ih, w_hh, b_ih, b_hh, H):
@@ -129,6 +129,7 @@ class B200GRU(nn.GRU):
         Hs = self.hidden_size
         flags = _default_flags()
         cluster = Hs in (128, 256) and T > 1 and not flags & _cabi.F_GENERIC_REC
+        infer = 0 if torch.is_grad_enabled() else _F_INFER   # no reserve for a backward under torch.no_grad()
         for layer in range(self.num_layers):
             if cluster:   # both directions in one launch on the cluster-resident kernels
                 ws = []
@@ -138,7 +139,7 @@ class B200GRU(nn.GRU):
                                              getattr(self, "bias_ih" + sfx) if self.bias else None,
                                              getattr(self, "bias_hh" + sfx) if self.bias else None, Hs)
                 h0 = None if hx is None else hx[layer * D:(layer + 1) * D]
-                x, hl, _ = _LSTMLayerFn.apply(x, h0, None, D, Hs, (flags & ~_cabi.F_BF16) | _cabi.F_GRU, *ws)
+                x, hl, _ = _LSTMLayerFn.apply(x, h0, None, D, Hs, (flags & ~_cabi.F_BF16) | _cabi.F_GRU | infer, *ws)
                 h_n += [hl[d] for d in range(D)]
                 if self.dropout > 0.0 and self.training and layer + 1 < self.num_layers:
                     x = F.dropout(x, self.dropout, True)

@@ -561,6 +561,22 @@ def test_gru_reduced_precision_tensor_core_recurrence(mode, B, T, bi):
         assert rel_l2(pm.grad.cpu(), pr.grad) <= 5e-2, name
 
 
+def test_gru_inference_under_no_grad_matches_torch():
+    """B200GRU on the cluster kernels under torch.no_grad() (inference flag: no reserve for a backward): fp64 nn.GRU."""
+    from multimodalreactiongeneration_b200 import B200GRU
+    torch.manual_seed(23)
+    ref = torch.nn.GRU(256, 256, 2, batch_first=True).double()
+    mine = B200GRU(256, 256, 2, batch_first=True)
+    mine.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mine = mine.cuda()
+    x = torch.randn(9, 31, 256, dtype=torch.double)
+    h0 = torch.randn(2, 9, 256, dtype=torch.double) * 0.5
+    with torch.no_grad():
+        yr, hr = ref(x, h0)
+        ym, hm = mine(x.float().cuda(), h0.float().cuda())
+    assert rel_err(ym.cpu(), yr) <= OUT_TOL and rel_err(hm.cpu(), hr) <= OUT_TOL
+
+
 def test_gru_mixer_layerd_matches_reference():
     from multimodalreactiongeneration_b200.mr_gen.model.utils.mixer_block import GRUMixerLayerd
     sd, ins, outs, grads, meta = load_golden("gru_mixer_layerd")
