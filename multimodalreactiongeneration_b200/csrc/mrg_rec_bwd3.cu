@@ -1,4 +1,4 @@
-// BPTT kernel for the REDUCED-PRECISION modes (tf32 / bf16) at many rows per cluster — the mirror of mrg_rec_fwd3.cu:
+// BPTT kernel for the REDUCED-PRECISION modes (tf32 / bf16) — the mirror of mrg_rec_fwd3.cu:
 // dh_{t-1} = dpre_t W_hh on the warp-level tensor cores.
 //
 // rec_bwd2_kernel (mrg_rec_bwd2.cu) multiplies with FFMA2 (exact fp32 products for the 1e-4 gradient budget of the fp32

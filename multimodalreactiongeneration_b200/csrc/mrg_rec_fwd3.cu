@@ -1,4 +1,4 @@
-// Recurrent forward kernel for the REDUCED-PRECISION modes (tf32 / bf16) at many rows per cluster: h_{t-1} W_hh^T on the
+// Recurrent forward kernel for the REDUCED-PRECISION modes (tf32 / bf16): h_{t-1} W_hh^T on the
 // warp-level tensor cores.
 //
 // rec_fwd2_kernel (mrg_rec_fwd2.cu) multiplies with FFMA2 because the fp32 mode has a 1e-5 parity budget per step: exact
