@@ -71,8 +71,9 @@ class MotionDecoder(nn.Module):
         return x[..., -1:, :]
 
     def forward(self, att_embedded: torch.Tensor) -> torch.Tensor:
-        y = self.decoder_lstm(att_embedded)[0]
-        return self.mapping(self.seq_reshape(y))
+        # reference: mapping(seq_reshape(decoder_lstm(x)[0])) — only the last frame of the decoder output is read, so the
+        # last block's per-token tail runs on that frame alone (same numbers, LSTMLayerd.forward_last_step)
+        return self.mapping(self.decoder_lstm.forward_last_step(att_embedded))
 
 
 class SimpleLSTM(LightningModule):

@@ -61,6 +61,26 @@ class LSTMBlock(nn.Module):
             y = self.feed_forward_module(y)
         return y, hx
 
+    def dropout_inactive(self) -> bool:
+        return not self.training or all(m.p == 0.0 for m in self.modules() if isinstance(m, nn.Dropout))
+
+    def forward_last_step(self, input_tenor: torch.Tensor, hx=None) -> torch.Tensor:
+        """``self.forward(x, hx)[0][..., -1:, :]``: the recurrence runs over the whole sequence, the per-token tail (mixer,
+        residual + LayerNorm, bottleneck FFN) only on the frame that is kept.  Exact while no dropout mask is drawn (a mask
+        of the sliced shape would be a different draw): callers check ``dropout_inactive()``."""
+        core = self.lstm_module
+        wrapped = isinstance(core, ResidualConnection)
+        mod = core.module if wrapped else core
+        hs, _ = mod.lstm_module(input_tenor, hx)
+        y = hs[..., -1:, :]
+        if mod.mixer is not None:
+            y = mod.mixer(y)
+        if wrapped:
+            y = core.finish(y, input_tenor[..., -1:, :])
+        if self.use_feed_forward:
+            y = self.feed_forward_module(y)
+        return y
+
 
 class LSTMLayerd(nn.Module):
     def __init__(self, input_size=256, lstm_hidden_size=128, affine_hidden_size=256, bottleneck_size=64,
@@ -86,3 +106,17 @@ class LSTMLayerd(nn.Module):
             x, _ = block(x, None if hxs is None else hxs[i])
         # the reference collects the new states but hands back its argument (lstm_block.py:164-169)
         return x, hxs
+
+    def forward_last_step(self, input_tensor: torch.Tensor, hxs: Optional[List[State]] = None) -> torch.Tensor:
+        """``self.forward(x, hxs)[0][..., -1:, :]`` — what the reference's MotionDecoder keeps of its decoder stack
+        (``seq_reshape``, simple_lstm.py:168-170) — without running the per-token tail of the LAST block on the T - 1
+        frames nobody reads (mixer Linear, residual + LayerNorm, bottleneck FFN and their backward GEMMs over [B, T, F]).
+        Per-token operators commute with the slice, so the kept frame and every gradient are the same numbers."""
+        blocks = self.lstm_layered
+        last = blocks[len(blocks) - 1]
+        if not last.dropout_inactive():
+            return self.forward(input_tensor, hxs)[0][..., -1:, :]
+        x = input_tensor
+        for i in range(len(blocks) - 1):
+            x, _ = blocks[i](x, None if hxs is None else hxs[i])
+        return last.forward_last_step(x, None if hxs is None else hxs[len(blocks) - 1])

@@ -24,6 +24,11 @@ class ResidualConnection(nn.Module):
         extras = None
         if isinstance(out, (tuple, list)):
             out, extras = out[0], tuple(out[1:])
+        out = self.finish(out, x)
+        return out if extras is None else (out, *extras)
+
+    def finish(self, out, x):
+        """Dropout(LN(out + x)): everything of ``forward`` behind the wrapped module (per-token)."""
         ln = self.layer_norm
         if ln is not None and ln.elementwise_affine and ln.bias is not None and _fused_ln.supported(out, x):
             # one pass over the [B, T, H] stream: add + LayerNorm fused, strides consumed in place
@@ -32,5 +37,4 @@ class ResidualConnection(nn.Module):
             out = out + x
             if ln is not None:
                 out = ln(out)
-        out = self.dropout(out)
-        return out if extras is None else (out, *extras)
+        return self.dropout(out)

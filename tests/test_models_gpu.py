@@ -48,6 +48,33 @@ def test_lstm_layerd_matches_reference(name, bi):
     _check_grads(m, grads)
 
 
+def test_layerd_last_step_equals_the_slice_of_the_full_forward():
+    """LSTMLayerd.forward_last_step (what MotionDecoder consumes) against forward(x)[0][:, -1:]: output and every gradient;
+    with an active dropout it must fall back to the full forward (same RNG stream as the reference)."""
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.lstm_block import LSTMLayerd
+    torch.manual_seed(3)
+    m = LSTMLayerd(input_size=256, lstm_hidden_size=256, affine_hidden_size=256, bottleneck_size=64, num_layers=2,
+                   output_size=256, bidirectional=False, use_mixing=True).cuda()
+    x = torch.randn(5, 37, 256, device="cuda")
+    w = torch.randn(5, 1, 256, device="cuda")
+    xa = x.clone().requires_grad_(True)
+    (m(xa)[0][:, -1:] * w).sum().backward()
+    ga = {n: p.grad.clone() for n, p in m.named_parameters()}
+    ya = m(xa)[0][:, -1:].detach()
+    for p in m.parameters():
+        p.grad = None
+    xb = x.clone().requires_grad_(True)
+    yb = m.forward_last_step(xb)
+    (yb * w).sum().backward()
+    assert rel_err(yb.detach().cpu(), ya.cpu().double()) <= OUT_TOL
+    assert rel_l2(xb.grad.cpu(), xa.grad.cpu().double()) <= GRAD_TOL
+    for n, p in m.named_parameters():
+        assert rel_l2(p.grad.cpu(), ga[n].cpu().double()) <= GRAD_TOL, n
+    md = LSTMLayerd(input_size=256, lstm_hidden_size=256, affine_hidden_size=256, num_layers=1, output_size=256,
+                    bidirectional=False, use_mixing=True, dropout=0.5).cuda().train()
+    assert not md.lstm_layered[0].dropout_inactive() and md.eval().lstm_layered[0].dropout_inactive()
+
+
 def test_lstm_sampler_matches_reference():
     from multimodalreactiongeneration_b200.mr_gen.model.utils import LSTMSampler
     sd, ins, outs, _, _ = load_golden("lstm_sampler")
