@@ -71,8 +71,14 @@ class LSTMBlock(nn.Module):
         core = self.lstm_module
         wrapped = isinstance(core, ResidualConnection)
         mod = core.module if wrapped else core
-        hs, _ = mod.lstm_module(input_tenor, hx)
-        y = hs[..., -1:, :]
+        hs, (h_n, _) = mod.lstm_module(input_tenor, hx)
+        lstm = mod.lstm_module
+        if not lstm.bidirectional and lstm.batch_first and input_tenor.dim() == 3:
+            # one direction: the last output frame IS the final hidden state of the top layer — taking it from h_n keeps
+            # the gradient out of a dense [B, T, H] zero tensor (it enters the BPTT kernel as dh_n; no dy stream at all)
+            y = h_n[-1].unsqueeze(1)
+        else:
+            y = hs[..., -1:, :]
         if mod.mixer is not None:
             y = mod.mixer(y)
         if wrapped:
