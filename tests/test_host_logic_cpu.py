@@ -141,3 +141,35 @@ def test_simple_lstm_and_mixer_stacks_host_logic_match_reference(torch_arithmeti
         (y * ins["w"]).sum().backward()
         assert hx is None and rel_err(y, outs["y"]) <= 1e-6 and rel_l2(x.grad, grads["x"]) <= 1e-5
         _grads_match(m, grads)
+
+
+@pytest.mark.parametrize("bi", [False, True])
+def test_layerd_last_step_host_logic(torch_arithmetic, bi):
+    """LSTMLayerd.forward_last_step (MotionDecoder's path) against the slice of the full forward, host logic on CPU: output,
+    input gradient and every parameter gradient; one direction takes the kept frame from h_n, two directions from the slice;
+    an active dropout falls back to the full forward (same RNG stream: identical draws under a fixed seed)."""
+    from multimodalreactiongeneration_b200.mr_gen.model.utils.lstm_block import LSTMLayerd
+    torch.manual_seed(5)
+    m = LSTMLayerd(input_size=16, lstm_hidden_size=8 if bi else 16, affine_hidden_size=16, bottleneck_size=4, num_layers=2,
+                   output_size=16, bidirectional=bi, use_mixing=True).double()
+    x = torch.randn(3, 11, 16, dtype=torch.double)
+    w = torch.randn(3, 1, 16, dtype=torch.double)
+    xa = x.clone().requires_grad_(True)
+    ya = m(xa)[0][:, -1:]
+    (ya * w).sum().backward()
+    ga = {n: p.grad.clone() for n, p in m.named_parameters()}
+    for p in m.parameters():
+        p.grad = None
+    xb = x.clone().requires_grad_(True)
+    yb = m.forward_last_step(xb)
+    (yb * w).sum().backward()
+    assert yb.shape == ya.shape and rel_err(yb.detach(), ya.detach()) <= 1e-12
+    assert rel_l2(xb.grad, xa.grad) <= 1e-12
+    for n, p in m.named_parameters():
+        assert rel_l2(p.grad, ga[n]) <= 1e-12, n
+    md = LSTMLayerd(input_size=16, lstm_hidden_size=16, affine_hidden_size=16, bottleneck_size=4, num_layers=2,
+                    output_size=16, bidirectional=False, use_mixing=True, dropout=0.3).double().train()
+    torch.manual_seed(9)
+    full = md(x)[0][:, -1:]
+    torch.manual_seed(9)
+    assert torch.equal(md.forward_last_step(x), full)
